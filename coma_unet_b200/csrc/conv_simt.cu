@@ -1,0 +1,242 @@
+// Direct (gather) 3-D convolution on CUDA cores, NDHWC, fp32 accumulate.
+//
+// Role on the hot path: (1) the exact-fp32 path (north_star's <=1e-4 tolerance), (2) shapes the
+// tcgen05 implicit GEMM does not take (Cin = 1 head conv, per-sample expert-mixed 1x1x1
+// `reduce_channels`, 1-channel heads), (3) on-device cross-check for the tensor-core kernels.
+// Replaces cuDNN fprop/dgrad/wgrad behind torch.nn.Conv3d / ConvTranspose3d
+// (reference call sites: attn_unet_data_parallel.py:126,285-306,442,495-497,546-558).
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int kSimtThreads = 128;
+
+template <typename T, int COT, int VEC>
+__global__ void __launch_bounds__(kSimtThreads) conv_simt_kernel(coma_conv_args a, int chunks) {
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const int64_t v = (int64_t)chunk * kSimtThreads + threadIdx.x;
+  const bool valid = v < Vo;
+  const int co0 = blockIdx.y * COT;
+  const int K = a.ksize;
+  float acc[COT];
+#pragma unroll
+  for (int j = 0; j < COT; ++j) acc[j] = 0.f;
+
+  if (valid) {
+    const int ow = (int)(v % a.Wo), oh = (int)((v / a.Wo) % a.Ho), od = (int)(v / ((int64_t)a.Wo * a.Ho));
+    const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.Di * a.Hi * a.Wi * a.x_cs + a.x_co;
+    const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride;
+    for (int kd = 0; kd < K; ++kd) {
+      int id;
+      if (!a.transposed) {
+        id = od * a.stride + kd - a.pad;
+      } else {
+        const int t = od + a.pad - kd;
+        if (t < 0 || (t % a.stride) != 0) continue;
+        id = t / a.stride;
+      }
+      if (id < 0 || id >= a.Di) continue;
+      for (int kh = 0; kh < K; ++kh) {
+        int ih;
+        if (!a.transposed) {
+          ih = oh * a.stride + kh - a.pad;
+        } else {
+          const int t = oh + a.pad - kh;
+          if (t < 0 || (t % a.stride) != 0) continue;
+          ih = t / a.stride;
+        }
+        if (ih < 0 || ih >= a.Hi) continue;
+        for (int kw = 0; kw < K; ++kw) {
+          int iw;
+          if (!a.transposed) {
+            iw = ow * a.stride + kw - a.pad;
+          } else {
+            const int t = ow + a.pad - kw;
+            if (t < 0 || (t % a.stride) != 0) continue;
+            iw = t / a.stride;
+          }
+          if (iw < 0 || iw >= a.Wi) continue;
+          const int tap = (kd * K + kh) * K + kw;
+          const T* xp = xb + (((int64_t)id * a.Hi + ih) * a.Wi + iw) * a.x_cs;
+          const T* wp = wb + ((int64_t)tap * a.Cout + co0) * a.Cin;
+          if (VEC == 8) {
+            for (int ci = 0; ci < a.Cin; ci += 8) {
+              float xv[8];
+              load8(xp + ci, xv);
+#pragma unroll
+              for (int j = 0; j < COT; ++j) {
+                if (co0 + j < a.Cout) {
+                  float wv[8];
+                  load8(wp + (int64_t)j * a.Cin + ci, wv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) acc[j] = fmaf(xv[e], wv[e], acc[j]);
+                }
+              }
+            }
+          } else {
+            for (int ci = 0; ci < a.Cin; ++ci) {
+              const float xs = Elem<T>::ld(xp + ci);
+#pragma unroll
+              for (int j = 0; j < COT; ++j)
+                if (co0 + j < a.Cout) acc[j] = fmaf(xs, Elem<T>::ld(wp + (int64_t)j * a.Cin + ci), acc[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: bias, statistics of the raw output, per-(sample,channel) affine + activation ----
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  __shared__ float red[kSimtThreads / 32][COT][2];
+  T* yp = static_cast<T*>(a.y) + ((int64_t)b * Vo + v) * a.y_cs + a.y_co;
+#pragma unroll
+  for (int j = 0; j < COT; ++j) {
+    const int co = co0 + j;
+    float val = 0.f;
+    if (co < a.Cout && valid) {
+      val = acc[j] + (a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride + co) : 0.f);
+      if (co < a.y_cn) {
+        float u = val;
+        if (a.scale) u = fmaf(__ldg(a.scale + (int64_t)b * a.Cout + co), val, __ldg(a.shift + (int64_t)b * a.Cout + co));
+        Elem<T>::st(yp + co, act_fwd(a.act, u, slope));
+      }
+    }
+    if (a.stats) {
+      const float s1 = warp_sum(val), s2 = warp_sum(val * val);
+      if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][j][0] = s1;
+        red[threadIdx.x >> 5][j][1] = s2;
+      }
+    }
+  }
+  if (a.stats) {
+    __syncthreads();
+    if (threadIdx.x < COT * 2) {
+      const int j = threadIdx.x >> 1, q = threadIdx.x & 1, co = co0 + j;
+      if (co < a.Cout) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSimtThreads / 32; ++w) s += red[w][j][q];
+        a.stats[(((int64_t)b * chunks + chunk) * a.Cout + co) * 2 + q] = s;
+      }
+    }
+  }
+}
+
+static int simt_chunks(const coma_conv_args& a) {
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  return (int)((Vo + kSimtThreads - 1) / kSimtThreads);
+}
+
+template <typename T>
+static int launch_simt_t(const coma_conv_args& a, cudaStream_t stream) {
+  const int chunks = simt_chunks(a);
+  const bool vec = (a.Cin % 8 == 0) && (a.x_cs % 8 == 0) && (a.x_co % 8 == 0) && (a.w_bstride % 8 == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.x) % 32 == 0) && (reinterpret_cast<uintptr_t>(a.w) % 32 == 0);
+  const bool wide = a.Cout >= 8;
+  dim3 grid((unsigned)(a.B * chunks), (unsigned)((a.Cout + (wide ? 8 : 1) - 1) / (wide ? 8 : 1)));
+  if (wide && vec) conv_simt_kernel<T, 8, 8><<<grid, kSimtThreads, 0, stream>>>(a, chunks);
+  else if (wide) conv_simt_kernel<T, 8, 1><<<grid, kSimtThreads, 0, stream>>>(a, chunks);
+  else if (vec) conv_simt_kernel<T, 1, 8><<<grid, kSimtThreads, 0, stream>>>(a, chunks);
+  else conv_simt_kernel<T, 1, 1><<<grid, kSimtThreads, 0, stream>>>(a, chunks);
+  COMA_CHECK_LAUNCH("conv_simt");
+  return COMA_OK;
+}
+
+int conv_simt_stat_chunks(const coma_conv_args& a) { return simt_chunks(a); }
+
+int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
+  if (a.dtype == COMA_BF16) return launch_simt_t<__nv_bfloat16>(a, stream);
+  return launch_simt_t<float>(a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dw[tap][cg][cx] += sum_o g[o][cg] * x[o*stride + k - pad][cx]   (split over voxels)
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgTile = 64, kWgVox = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(coma_wgrad_args a, int64_t vchunk, int cx_tiles) {
+  __shared__ float sg[kWgVox][kWgTile + 4];
+  __shared__ float sx[kWgVox][kWgTile + 4];
+  const int K = a.ksize;
+  const int tap = blockIdx.y;
+  const int kd = tap / (K * K), kh = (tap / K) % K, kw = tap % K;
+  const int cg0 = (blockIdx.z / cx_tiles) * kWgTile, cx0 = (blockIdx.z % cx_tiles) * kWgTile;
+  const int64_t Vg = (int64_t)a.Dg * a.Hg * a.Wg, total = (int64_t)a.B * Vg;
+  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, total);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const T* gp = static_cast<const T*>(a.g);
+  const T* xp = static_cast<const T*>(a.x);
+  for (int64_t base = begin; base < end; base += kWgVox) {
+    // 16 voxels x 64 channels per operand, 4 elements per thread each
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = r * 256 + threadIdx.x;
+      const int vv = idx >> 6, c = idx & 63;
+      const int64_t o = base + vv;
+      float gval = 0.f, xval = 0.f;
+      if (o < end) {
+        if (cg0 + c < a.Cg) gval = Elem<T>::ld(gp + o * a.g_cs + a.g_co + cg0 + c);
+        if (cx0 + c < a.Cx) {
+          const int64_t bb = o / Vg, rem = o % Vg;
+          const int ow = (int)(rem % a.Wg), oh = (int)((rem / a.Wg) % a.Hg), od = (int)(rem / ((int64_t)a.Wg * a.Hg));
+          const int id = od * a.stride + kd - a.pad, ih = oh * a.stride + kh - a.pad, iw = ow * a.stride + kw - a.pad;
+          if (id >= 0 && id < a.Dx && ih >= 0 && ih < a.Hx && iw >= 0 && iw < a.Wx)
+            xval = Elem<T>::ld(xp + (((bb * a.Dx + id) * a.Hx + ih) * a.Wx + iw) * a.x_cs + a.x_co + cx0 + c);
+        }
+      }
+      sg[vv][c] = gval;
+      sx[vv][c] = xval;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int vv = 0; vv < kWgVox; ++vv) {
+      float gv[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gv[i] = sg[vv][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = sx[vv][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cg = cg0 + ty * 4 + i;
+    if (cg >= a.Cg) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cx = cx0 + tx * 4 + j;
+      if (cx < a.Cx) atomicAdd(a.dw + ((int64_t)tap * a.Cg + cg) * a.Cx + cx, acc[i][j]);
+    }
+  }
+}
+
+int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
+  int64_t nchunks = (total + 255) / 256;
+  if (nchunks > 512) nchunks = 512;
+  int64_t vchunk = (total + nchunks - 1) / nchunks;
+  vchunk = (vchunk + kWgVox - 1) / kWgVox * kWgVox;
+  nchunks = (total + vchunk - 1) / vchunk;
+  const int cg_tiles = (a.Cg + kWgTile - 1) / kWgTile, cx_tiles = (a.Cx + kWgTile - 1) / kWgTile;
+  dim3 grid((unsigned)nchunks, (unsigned)(a.ksize * a.ksize * a.ksize), (unsigned)(cg_tiles * cx_tiles));
+  if (a.dtype == COMA_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, vchunk, cx_tiles);
+  else wgrad_simt_kernel<float><<<grid, 256, 0, stream>>>(a, vchunk, cx_tiles);
+  COMA_CHECK_LAUNCH("wgrad_simt");
+  return COMA_OK;
+}
+
+}  // namespace coma

@@ -1,0 +1,480 @@
+// Normalisation statistics, FiLM/affine + activation apply, and their backward.  HBM-bound kernels:
+// every pass is one coalesced, 16-byte-vectorised sweep over an NDHWC tensor with warp-shuffle /
+// shared-memory reductions.  Replaces the BatchNorm3d / InstanceNorm3d / PReLU / ReLU / LeakyReLU
+// kernel chains of MONAI's ADN (reference: attn_unet_data_parallel.py:285-306,495-497,558; MONAI
+// blocks/acti_norm.py) plus the missing CondConv modulation (oracle/cond_conv.py).
+//
+// Algorithmic bytes per element (s = sizeof(T)):  stats: s read;  apply fwd: s read + s write;
+// bwd reduce: 2s read;  bwd apply: 2s read + s write.
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int kThreads = 256;
+
+static int stats_chunks(int64_t V) {
+  int64_t c = (V + 2047) / 2048;
+  return (int)(c < 1 ? 1 : (c > 256 ? 256 : c));
+}
+
+// ---- per-(b, chunk, c) partial sums ------------------------------------------------------------
+// NQ = 2: (sum x, sum x^2).   NQ = 3 (backward): (sum dz, sum dz*xhat, sum_{u<0} dy*u)
+struct BwdCtx {
+  const void* dy; const float* A; const float* S; const float* mean; const float* rstd; const float* slope;
+  int dy_cs, dy_co, act;
+  const void* r; int r_cs;   // optional residual added before the activation: u = A*x + S + r
+};
+
+template <typename T, int NQ>
+__device__ __forceinline__ void accumulate8(const float (&xv)[8], const float (&dyv)[8], const float (&rv)[8], const float* A8,
+                                            const float* S8, const float* M8, const float* R8, int act, float slope,
+                                            float (&acc)[8][NQ]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (NQ == 2) {
+      acc[e][0] += xv[e];
+      acc[e][1] += xv[e] * xv[e];
+    } else {
+      const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
+      const float dz = dyv[e] * act_grad(act, u, slope);
+      acc[e][0] += dz;
+      acc[e][1] += dz * (xv[e] - M8[e]) * R8[e];
+      if (NQ > 2) acc[e][NQ - 1] += dyv[e] * act_slope_grad(act, u, slope);
+    }
+  }
+}
+
+template <typename T, int NQ>
+__global__ void __launch_bounds__(kThreads) reduce_vec_kernel(const T* __restrict__ x, int64_t V, int C, int cs, int co,
+                                                              int chunks, float* __restrict__ partial, BwdCtx ctx) {
+  extern __shared__ float red[];  // [kThreads][8*NQ]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int CV = C >> 3, lanes = kThreads / CV;
+  const int cvec = threadIdx.x % CV, vlane = threadIdx.x / CV;
+  const int64_t per = (V + chunks - 1) / chunks, v0 = (int64_t)chunk * per, v1 = min(v0 + per, V);
+  float acc[8][NQ];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[e][q] = 0.f;
+  float A8[8], S8[8], M8[8], R8[8];
+  float slope = 0.f;
+  if (NQ == 3) {
+    const int64_t o = (int64_t)b * C + cvec * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      A8[e] = ctx.A[o + e]; S8[e] = ctx.S[o + e]; M8[e] = ctx.mean[o + e]; R8[e] = ctx.rstd[o + e];
+    }
+    slope = ctx.slope ? __ldg(ctx.slope) : 0.f;
+  }
+  const T* xb = x + (int64_t)b * V * cs + co + cvec * 8;
+  const T* dyb = NQ == 3 ? static_cast<const T*>(ctx.dy) + (int64_t)b * V * ctx.dy_cs + ctx.dy_co + cvec * 8 : nullptr;
+  const T* rb = (NQ == 3 && ctx.r) ? static_cast<const T*>(ctx.r) + (int64_t)b * V * ctx.r_cs + cvec * 8 : nullptr;
+  if (vlane < lanes) {
+    for (int64_t v = v0 + vlane; v < v1; v += lanes) {
+      float xv[8], dyv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      load8(xb + v * cs, xv);
+      if (NQ == 3) load8(dyb + v * ctx.dy_cs, dyv);
+      if (NQ == 3 && rb) load8(rb + v * ctx.r_cs, rv);
+      accumulate8<T, NQ>(xv, dyv, rv, A8, S8, M8, R8, ctx.act, slope, acc);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) red[threadIdx.x * 8 * NQ + e * NQ + q] = acc[e][q];
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * NQ; i += kThreads) {
+    const int c = i / NQ, q = i % NQ;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(l * CV + (c >> 3)) * 8 * NQ + (c & 7) * NQ + q];
+    partial[(((int64_t)b * chunks + chunk) * C + c) * NQ + q] = s;
+  }
+}
+
+// scalar variant for C < 8 (1-channel volumes of the modulator stacks and heads)
+template <typename T, int NQ>
+__global__ void __launch_bounds__(kThreads) reduce_small_kernel(const T* __restrict__ x, int64_t V, int C, int cs, int co,
+                                                                int chunks, float* __restrict__ partial, BwdCtx ctx) {
+  __shared__ float red[kThreads / 32][8][NQ];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (V + chunks - 1) / chunks, v0 = (int64_t)chunk * per, v1 = min(v0 + per, V);
+  float acc[8][NQ];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[e][q] = 0.f;
+  const float slope = (NQ == 3 && ctx.slope) ? __ldg(ctx.slope) : 0.f;
+  const T* xb = x + (int64_t)b * V * cs + co;
+  const T* dyb = NQ == 3 ? static_cast<const T*>(ctx.dy) + (int64_t)b * V * ctx.dy_cs + ctx.dy_co : nullptr;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < C) {
+        const float xv = Elem<T>::ld(xb + v * cs + c);
+        if (NQ == 2) {
+          acc[c][0] += xv;
+          acc[c][1] += xv * xv;
+        } else {
+          const int64_t o = (int64_t)b * C + c;
+          const float u = fmaf(ctx.A[o], xv, ctx.S[o]) +
+                          (ctx.r ? Elem<T>::ld(static_cast<const T*>(ctx.r) + ((int64_t)b * V + v) * ctx.r_cs + c) : 0.f);
+          const float dyv = Elem<T>::ld(dyb + v * ctx.dy_cs + c);
+          const float dz = dyv * act_grad(ctx.act, u, slope);
+          acc[c][0] += dz;
+          acc[c][1] += dz * (xv - ctx.mean[o]) * ctx.rstd[o];
+          acc[c][NQ - 1] += dyv * act_slope_grad(ctx.act, u, slope);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float s = warp_sum(acc[c][q]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c][q] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < C * NQ) {
+    const int c = threadIdx.x / NQ, q = threadIdx.x % NQ;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][c][q];
+    partial[(((int64_t)b * chunks + chunk) * C + c) * NQ + q] = s;
+  }
+}
+
+static bool vec_ok(const void* p, int C, int cs, int co, int dtype) {
+  const int esz = dtype == COMA_BF16 ? 2 : 4;
+  return C >= 8 && (C % 8 == 0) && (kThreads % (C / 8) == 0) && (cs % 8 == 0) && (co % 8 == 0) &&
+         (reinterpret_cast<uintptr_t>(p) % (8 * esz > 16 ? 16 : 8 * esz) == 0);
+}
+
+template <typename T, int NQ>
+static int launch_reduce(const void* x, int B, int64_t V, int C, int cs, int co, int dtype, int chunks, float* partial,
+                         const BwdCtx& ctx, cudaStream_t stream) {
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  bool v = vec_ok(x, C, cs, co, dtype);
+  if (NQ == 3) v = v && vec_ok(ctx.dy, C, ctx.dy_cs, ctx.dy_co, dtype) && (!ctx.r || vec_ok(ctx.r, C, ctx.r_cs, 0, dtype));
+  if (v) {
+    const size_t smem = (size_t)kThreads * 8 * NQ * sizeof(float);
+    reduce_vec_kernel<T, NQ><<<grid, kThreads, smem, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
+  } else {
+    COMA_CHECK_ARG(C <= 8, "norm reduce: C=%d must be a power-of-two multiple of 8 (aligned) or <= 8", C);
+    reduce_small_kernel<T, NQ><<<grid, kThreads, 0, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
+  }
+  COMA_CHECK_LAUNCH("norm_reduce");
+  return COMA_OK;
+}
+
+// ---- forward finalize ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) finalize_kernel(coma_norm_finalize_args a) {
+  // INSTANCE: one block per (b, c).  BATCH: one block per c.  NONE / GIVEN: one thread per (b, c).
+  __shared__ double sh[2][kThreads / 32];
+  const int B = a.B, C = a.C;
+  if (a.mode == COMA_NORM_NONE || a.mode == COMA_NORM_GIVEN) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= B * C) return;
+    const int c = i % C;
+    float mean = 0.f, rstd = 1.f;
+    if (a.mode == COMA_NORM_GIVEN) {
+      mean = a.given_mean[c];
+      rstd = rsqrtf(a.given_var[c] + a.eps);
+    }
+    const float g = a.g ? a.g[i] : 1.f, h = a.h ? a.h[i] : 0.f;
+    a.A[i] = g * rstd;
+    a.S[i] = h - g * rstd * mean;
+    a.mean[i] = mean;
+    a.rstd[i] = rstd;
+    return;
+  }
+  const bool batch = a.mode == COMA_NORM_BATCH;
+  const int c = batch ? blockIdx.x : blockIdx.x % C;
+  const int b0 = batch ? 0 : blockIdx.x / C, b1 = batch ? B : b0 + 1;
+  double s1 = 0.0, s2 = 0.0;
+  const int n = (b1 - b0) * a.chunks;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const int b = b0 + i / a.chunks, ch = i % a.chunks;
+    const float* p = a.partial + (((int64_t)b * a.chunks + ch) * C + c) * 2;
+    s1 += p[0];
+    s2 += p[1];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s1;
+    sh[1][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s1 = 0.0; s2 = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { s1 += sh[0][w]; s2 += sh[1][w]; }
+    const double cnt = (double)(b1 - b0) * (double)a.V;
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    for (int b = b0; b < b1; ++b) {
+      const int i = b * C + c;
+      const float g = a.g ? a.g[i] : 1.f, h = a.h ? a.h[i] : 0.f;
+      a.A[i] = g * rstd;
+      a.S[i] = h - g * rstd * (float)mean;
+      a.mean[i] = (float)mean;
+      a.rstd[i] = rstd;
+    }
+    if (batch && a.running_mean) {
+      const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+      float rm = a.running_mean[c], rv = a.running_var[c];
+      for (int u = 0; u < a.n_updates; ++u) {
+        rm = (1.f - a.momentum) * rm + a.momentum * (float)mean;
+        rv = (1.f - a.momentum) * rv + a.momentum * (float)unbiased;
+      }
+      a.running_mean[c] = rm;
+      a.running_var[c] = rv;
+    }
+  }
+}
+
+// ---- apply: y = act(A*x + S) ---------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_act_args a, int chunks) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int CV = a.C >> 3, lanes = kThreads / CV;
+  const int cvec = threadIdx.x % CV, vlane = threadIdx.x / CV;
+  if (vlane >= lanes) return;
+  const int64_t per = (a.V + chunks - 1) / chunks, v0 = (int64_t)chunk * per, v1 = min(v0 + per, a.V);
+  float A8[8], S8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    A8[e] = a.A[(int64_t)b * a.C + cvec * 8 + e];
+    S8[e] = a.S[(int64_t)b * a.C + cvec * 8 + e];
+  }
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co + cvec * 8;
+  T* yb = static_cast<T*>(a.y) + (int64_t)b * a.V * a.y_cs + a.y_co + cvec * 8;
+  const T* rb = a.r ? static_cast<const T*>(a.r) + (int64_t)b * a.V * a.r_cs + cvec * 8 : nullptr;
+  for (int64_t v = v0 + vlane; v < v1; v += lanes) {
+    float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    load8(xb + v * a.x_cs, xv);
+    if (rb) load8(rb + v * a.r_cs, rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] = act_fwd(a.act, fmaf(A8[e], xv[e], S8[e]) + rv[e], slope);
+    store8(yb + v * a.y_cs, xv);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) affine_act_small_kernel(coma_affine_act_args a) {
+  const int b = blockIdx.y;
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co;
+  T* yb = static_cast<T*>(a.y) + (int64_t)b * a.V * a.y_cs + a.y_co;
+  for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * kThreads)
+    for (int c = 0; c < a.C; ++c) {
+      const float u = fmaf(a.A[(int64_t)b * a.C + c], Elem<T>::ld(xb + v * a.x_cs + c), a.S[(int64_t)b * a.C + c]) +
+                      (a.r ? Elem<T>::ld(static_cast<const T*>(a.r) + ((int64_t)b * a.V + v) * a.r_cs + c) : 0.f);
+      Elem<T>::st(yb + v * a.y_cs + c, act_fwd(a.act, u, slope));
+    }
+}
+
+// ---- backward finalize: partial sums -> dg, dh, dslope and dx = P*dz + Q + R*x coefficients -------
+__global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(coma_affine_act_bwd_args a, int chunks) {
+  // one block per channel c; threads stride over (b, chunk)
+  __shared__ float sh[kThreads / 32];
+  __shared__ float tot[3];
+  const int c = blockIdx.x, B = a.B, C = a.C;
+  float m1 = 0.f, m2 = 0.f, ds = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int ch = threadIdx.x; ch < chunks; ch += kThreads) {
+      const float* p = a.partial + (((int64_t)b * chunks + ch) * C + c) * 3;
+      s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+    }
+    for (int q = 0; q < 3; ++q) {
+      float v = warp_sum(s[q]);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+        tot[q] = t;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int i = b * C + c;
+      const float g = a.g ? a.g[i] : 1.f;
+      a.dh[i] = tot[0];
+      a.dg[i] = tot[1];
+      m1 += g * tot[0];
+      m2 += g * tot[1];
+      ds += tot[2];
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (a.dslope && (a.act == COMA_ACT_LEAKY || a.act == COMA_ACT_LEAKY_RELU)) atomicAdd(a.dslope, ds);
+    const float invBV = 1.f / ((float)B * (float)a.V), invV = 1.f / (float)a.V;
+    for (int b = 0; b < B; ++b) {
+      const int i = b * C + c;
+      const float g = a.g ? a.g[i] : 1.f;
+      const float P = a.A[i], rstd = a.rstd[i], mean = a.mean[i];
+      float R = 0.f, Q = 0.f;
+      if (a.mode == COMA_NORM_INSTANCE) {
+        R = -P * rstd * a.dg[i] * invV;
+        Q = -P * a.dh[i] * invV - R * mean;
+      } else if (a.mode == COMA_NORM_BATCH) {
+        R = -rstd * rstd * m2 * invBV;
+        Q = -rstd * m1 * invBV - R * mean;
+      }
+      (void)g;
+      a.coef[i * 3 + 0] = P;
+      a.coef[i * 3 + 1] = Q;
+      a.coef[i * 3 + 2] = R;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bwd_apply_vec_kernel(coma_affine_act_bwd_args a, int chunks) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int CV = a.C >> 3, lanes = kThreads / CV;
+  const int cvec = threadIdx.x % CV, vlane = threadIdx.x / CV;
+  if (vlane >= lanes) return;
+  const int64_t per = (a.V + chunks - 1) / chunks, v0 = (int64_t)chunk * per, v1 = min(v0 + per, a.V);
+  float A8[8], S8[8], P8[8], Q8[8], R8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int64_t i = (int64_t)b * a.C + cvec * 8 + e;
+    A8[e] = a.A[i]; S8[e] = a.S[i];
+    P8[e] = a.coef[i * 3]; Q8[e] = a.coef[i * 3 + 1]; R8[e] = a.coef[i * 3 + 2];
+  }
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co + cvec * 8;
+  const T* dyb = static_cast<const T*>(a.dy) + (int64_t)b * a.V * a.dy_cs + a.dy_co + cvec * 8;
+  T* dxb = static_cast<T*>(a.dx) + (int64_t)b * a.V * a.dx_cs + a.dx_co + cvec * 8;
+  const T* rb = a.r ? static_cast<const T*>(a.r) + (int64_t)b * a.V * a.r_cs + cvec * 8 : nullptr;
+  T* drb = a.dr ? static_cast<T*>(a.dr) + (int64_t)b * a.V * a.dr_cs + cvec * 8 : nullptr;
+  for (int64_t v = v0 + vlane; v < v1; v += lanes) {
+    float xv[8], dyv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    load8(xb + v * a.x_cs, xv);
+    load8(dyb + v * a.dy_cs, dyv);
+    if (rb) load8(rb + v * a.r_cs, rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
+      const float dz = dyv[e] * act_grad(a.act, u, slope);
+      xv[e] = fmaf(P8[e], dz, fmaf(R8[e], xv[e], Q8[e]));
+      rv[e] = dz;
+    }
+    store8(dxb + v * a.dx_cs, xv);
+    if (drb) store8(drb + v * a.dr_cs, rv);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bwd_apply_small_kernel(coma_affine_act_bwd_args a) {
+  const int b = blockIdx.y;
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co;
+  const T* dyb = static_cast<const T*>(a.dy) + (int64_t)b * a.V * a.dy_cs + a.dy_co;
+  T* dxb = static_cast<T*>(a.dx) + (int64_t)b * a.V * a.dx_cs + a.dx_co;
+  for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * kThreads)
+    for (int c = 0; c < a.C; ++c) {
+      const int64_t i = (int64_t)b * a.C + c;
+      const float xv = Elem<T>::ld(xb + v * a.x_cs + c);
+      const float u = fmaf(a.A[i], xv, a.S[i]) +
+                      (a.r ? Elem<T>::ld(static_cast<const T*>(a.r) + ((int64_t)b * a.V + v) * a.r_cs + c) : 0.f);
+      const float dz = Elem<T>::ld(dyb + v * a.dy_cs + c) * act_grad(a.act, u, slope);
+      Elem<T>::st(dxb + v * a.dx_cs + c, fmaf(a.coef[i * 3], dz, fmaf(a.coef[i * 3 + 2], xv, a.coef[i * 3 + 1])));
+      if (a.dr) Elem<T>::st(static_cast<T*>(a.dr) + ((int64_t)b * a.V + v) * a.dr_cs + c, dz);
+    }
+}
+
+}  // namespace coma
+
+using namespace coma;
+
+extern "C" int coma_norm_stats_chunks(int64_t V) { return stats_chunks(V); }
+
+extern "C" int coma_norm_stats(const void* x, int32_t B, int64_t V, int32_t C, int32_t cs, int32_t co, int32_t dtype,
+                               float* partial, coma_stream_t stream) {
+  COMA_CHECK_ARG(x && partial && B > 0 && V > 0 && C > 0, "coma_norm_stats: bad arguments");
+  BwdCtx ctx{};
+  const int chunks = stats_chunks(V);
+  if (dtype == COMA_BF16) return launch_reduce<__nv_bfloat16, 2>(x, B, V, C, cs, co, dtype, chunks, partial, ctx, stream);
+  return launch_reduce<float, 2>(x, B, V, C, cs, co, dtype, chunks, partial, ctx, stream);
+}
+
+extern "C" int coma_gate_stats(const void* x, int32_t B, int64_t V, int32_t C, int32_t cs, int32_t co, int32_t dtype,
+                               float* partial, coma_stream_t stream) {
+  return coma_norm_stats(x, B, V, C, cs, co, dtype, partial, stream);
+}
+
+extern "C" int coma_norm_stats_finalize(const coma_norm_finalize_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->A && a->S && a->mean && a->rstd && a->B > 0 && a->C > 0, "coma_norm_stats_finalize: bad arguments");
+  unsigned blocks;
+  if (a->mode == COMA_NORM_NONE || a->mode == COMA_NORM_GIVEN) {
+    COMA_CHECK_ARG(a->mode == COMA_NORM_NONE || (a->given_mean && a->given_var), "finalize: GIVEN needs mean/var");
+    blocks = (unsigned)((a->B * a->C + kThreads - 1) / kThreads);
+  } else {
+    COMA_CHECK_ARG(a->partial && a->chunks > 0 && a->V > 0, "finalize: partial sums missing");
+    blocks = (unsigned)(a->mode == COMA_NORM_BATCH ? a->C : a->B * a->C);
+  }
+  finalize_kernel<<<blocks, kThreads, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("norm_finalize");
+  return COMA_OK;
+}
+
+extern "C" int coma_norm_film_act_fwd(const coma_affine_act_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->x && a->y && a->A && a->S && a->B > 0 && a->C > 0 && a->V > 0, "coma_norm_film_act_fwd: bad arguments");
+  const bool vec = vec_ok(a->x, a->C, a->x_cs, a->x_co, a->dtype) && vec_ok(a->y, a->C, a->y_cs, a->y_co, a->dtype) &&
+                   (!a->r || vec_ok(a->r, a->C, a->r_cs, 0, a->dtype));
+  if (vec) {
+    const int chunks = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
+    dim3 grid((unsigned)chunks, (unsigned)a->B);
+    if (a->dtype == COMA_BF16) affine_act_vec_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a, chunks);
+    else affine_act_vec_kernel<float><<<grid, kThreads, 0, stream>>>(*a, chunks);
+  } else {
+    COMA_CHECK_ARG(a->C <= 64, "coma_norm_film_act_fwd: unaligned C=%d too large for the scalar path", a->C);
+    dim3 grid((unsigned)std::min<int64_t>((a->V + kThreads - 1) / kThreads, 2048), (unsigned)a->B);
+    if (a->dtype == COMA_BF16) affine_act_small_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a);
+    else affine_act_small_kernel<float><<<grid, kThreads, 0, stream>>>(*a);
+  }
+  COMA_CHECK_LAUNCH("affine_act_fwd");
+  return COMA_OK;
+}
+
+extern "C" int coma_norm_film_act_bwd(const coma_affine_act_bwd_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->x && a->dy && a->dx && a->A && a->S && a->mean && a->rstd && a->partial && a->dg && a->dh && a->coef,
+                 "coma_norm_film_act_bwd: bad arguments");
+  const int chunks = stats_chunks(a->V);
+  BwdCtx ctx{a->dy, a->A, a->S, a->mean, a->rstd, a->slope, a->dy_cs, a->dy_co, a->act, a->r, a->r_cs};
+  int rc;
+  if (a->dtype == COMA_BF16)
+    rc = launch_reduce<__nv_bfloat16, 3>(a->x, a->B, a->V, a->C, a->x_cs, a->x_co, a->dtype, chunks, a->partial, ctx, stream);
+  else
+    rc = launch_reduce<float, 3>(a->x, a->B, a->V, a->C, a->x_cs, a->x_co, a->dtype, chunks, a->partial, ctx, stream);
+  if (rc) return rc;
+  bwd_finalize_kernel<<<(unsigned)a->C, kThreads, 0, stream>>>(*a, chunks);
+  COMA_CHECK_LAUNCH("norm_bwd_finalize");
+  const bool vec = vec_ok(a->x, a->C, a->x_cs, a->x_co, a->dtype) && vec_ok(a->dy, a->C, a->dy_cs, a->dy_co, a->dtype) &&
+                   vec_ok(a->dx, a->C, a->dx_cs, a->dx_co, a->dtype) && (!a->r || vec_ok(a->r, a->C, a->r_cs, 0, a->dtype)) &&
+                   (!a->dr || vec_ok(a->dr, a->C, a->dr_cs, 0, a->dtype));
+  if (vec) {
+    const int ach = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
+    dim3 grid((unsigned)ach, (unsigned)a->B);
+    if (a->dtype == COMA_BF16) bwd_apply_vec_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a, ach);
+    else bwd_apply_vec_kernel<float><<<grid, kThreads, 0, stream>>>(*a, ach);
+  } else {
+    COMA_CHECK_ARG(a->C <= 64, "coma_norm_film_act_bwd: unaligned C=%d too large for the scalar path", a->C);
+    dim3 grid((unsigned)std::min<int64_t>((a->V + kThreads - 1) / kThreads, 2048), (unsigned)a->B);
+    if (a->dtype == COMA_BF16) bwd_apply_small_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a);
+    else bwd_apply_small_kernel<float><<<grid, kThreads, 0, stream>>>(*a);
+  }
+  COMA_CHECK_LAUNCH("affine_act_bwd");
+  return COMA_OK;
+}

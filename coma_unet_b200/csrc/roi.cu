@@ -1,0 +1,224 @@
+// ROI painting, prompt packing and the RoiMSE loss: the HBM-bound glue around the modulator stacks.
+//  - coma_roi_paint     replaces the B x 36 masked index_put_ loop + .item() syncs of
+//                       forward_modulator_with_uq (attn_unet_data_parallel.py:632-649)
+//  - coma_pack2_*       replace `general_prompt + ...` and the torch.cat calls (:651,654)
+//  - coma_roi_mse_*     replace RoiMSE.forward (criterions.py:181-211; ~40 ATen kernels + 2 syncs)
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int kMaxRoi = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) roi_paint_kernel(coma_roi_paint_args a) {
+  __shared__ float ids[kMaxRoi];
+  __shared__ float lut[kMaxRoi * 2];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < a.n_roi; i += 256) {
+    ids[i] = (float)a.roi_ids[i];
+    lut[2 * i] = a.lut[((int64_t)b * a.n_roi + i) * 2];
+    lut[2 * i + 1] = a.lut[((int64_t)b * a.n_roi + i) * 2 + 1];
+  }
+  __syncthreads();
+  const bool pos = a.is_pos[b] == 1.0f;
+  const float* prompt = pos ? a.pos_prompt : a.neg_prompt;
+  T* ob = static_cast<T*>(a.out) + (int64_t)b * a.V * a.out_cs;
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * 256) {
+    const float label = __ldg(a.roi + (int64_t)b * a.V + v);
+    float loc = 0.f, sd = 0.f;
+    if (!(__ldg(a.mri + (int64_t)b * a.V + v) < 1e-4f)) {
+      for (int i = 0; i < a.n_roi; ++i)
+        if (label == ids[i]) { loc = lut[2 * i]; sd = lut[2 * i + 1]; }
+    }
+    T* o = ob + v * a.out_cs;
+    Elem<T>::st(o, __ldg(prompt + v));
+    if (a.out_cs > 1) Elem<T>::st(o + 1, sd);
+    if (a.out_cs > 2) Elem<T>::st(o + 2, loc);
+    for (int c = 3; c < a.out_cs; ++c) Elem<T>::st(o + c, 0.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) roi_paint_bwd_kernel(const T* __restrict__ dbuf, const float* __restrict__ is_pos,
+                                                            float* __restrict__ dpos, float* __restrict__ dneg, int B,
+                                                            int64_t V, int cs) {
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    float p = 0.f, n = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float d = Elem<T>::ld(dbuf + ((int64_t)b * V + v) * cs);
+      if (is_pos[b] == 1.0f) p += d; else n += d;
+    }
+    dpos[v] = p;
+    dneg[v] = n;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack2_kernel(coma_pack2_args a) {
+  const int64_t total = (int64_t)a.B * a.V;
+  const T* pa = static_cast<const T*>(a.a);
+  const T* pb = static_cast<const T*>(a.b);
+  T* d = static_cast<T*>(a.dst);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t v = i % a.V;
+    T* o = d + i * a.dst_cs;
+    Elem<T>::st(o, Elem<T>::ld(pa + i) + (a.a_add ? __ldg(a.a_add + v) : 0.f));
+    Elem<T>::st(o + 1, Elem<T>::ld(pb + i));
+    for (int c = 2; c < a.dst_cs; ++c) Elem<T>::st(o + c, 0.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpack2_kernel(coma_unpack2_args a) {
+  const T* d = static_cast<const T*>(a.ddst);
+  T* da = static_cast<T*>(a.da);
+  T* db = static_cast<T*>(a.db);
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int b = 0; b < a.B; ++b) {
+      const int64_t i = (int64_t)b * a.V + v;
+      const float g0 = Elem<T>::ld(d + i * a.dst_cs), g1 = Elem<T>::ld(d + i * a.dst_cs + 1);
+      if (da) Elem<T>::st(da + i, g0);
+      if (db) Elem<T>::st(db + i, g1);
+      s += g0;
+    }
+    if (a.d_a_add) a.d_a_add[v] = s;
+  }
+}
+
+// ---- RoiMSE ------------------------------------------------------------------------------------
+static int mse_chunks(int64_t V) {
+  int64_t c = (V + 4095) / 4096;
+  return (int)(c < 1 ? 1 : (c > 512 ? 512 : c));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) roi_mse_partial_kernel(coma_roi_mse_args a, int chunks) {
+  __shared__ float ids[kMaxRoi], wts[kMaxRoi];
+  __shared__ float red[2][8];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  for (int i = threadIdx.x; i < a.n_roi; i += 256) {
+    ids[i] = (float)a.roi_ids[i];
+    wts[i] = a.roi_w[i];
+  }
+  __syncthreads();
+  const int64_t per = (a.V + chunks - 1) / chunks, v0 = (int64_t)chunk * per, v1 = min(v0 + per, a.V);
+  const T* pred = static_cast<const T*>(a.pred) + (int64_t)b * a.V;
+  float sq = 0.f, mk = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    const float d = Elem<T>::ld(pred + v) - __ldg(a.gt + (int64_t)b * a.V + v);
+    sq = fmaf(d, d, sq);
+    const float label = __ldg(a.roi + (int64_t)b * a.V + v);
+    float w = 0.f;
+    for (int i = 0; i < a.n_roi; ++i)
+      if (label == ids[i]) w = wts[i];
+    mk += w;
+  }
+  sq = warp_sum(sq);
+  mk = warp_sum(mk);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sq; red[1][threadIdx.x >> 5] = mk; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    a.partial[((int64_t)b * chunks + chunk) * 2 + threadIdx.x] = s;
+  }
+}
+
+__global__ void roi_mse_finalize_kernel(coma_roi_mse_args a, int chunks) {
+  const int b = blockIdx.x;
+  double sq = 0.0, mk = 0.0;
+  for (int i = threadIdx.x; i < chunks; i += 32) {
+    sq += a.partial[((int64_t)b * chunks + i) * 2];
+    mk += a.partial[((int64_t)b * chunks + i) * 2 + 1];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    mk += __shfl_xor_sync(0xffffffffu, mk, o);
+  }
+  if (threadIdx.x == 0) {
+    a.sums[2 * b] = (float)sq;
+    a.sums[2 * b + 1] = (float)mk;
+    a.loss[b] = (float)((mk / (double)a.V) * (sq / (double)a.V));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) roi_mse_bwd_kernel(coma_roi_mse_args a) {
+  const int b = blockIdx.y;
+  const float invV = 1.f / (float)a.V;
+  const float k = a.dloss[b] * a.sums[2 * b + 1] * invV * 2.f * invV;
+  const T* pred = static_cast<const T*>(a.pred) + (int64_t)b * a.V;
+  T* dp = static_cast<T*>(a.dpred) + (int64_t)b * a.V;
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * 256)
+    Elem<T>::st(dp + v, k * (Elem<T>::ld(pred + v) - __ldg(a.gt + (int64_t)b * a.V + v)));
+}
+
+static unsigned sweep_blocks(int64_t n) { return (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8); }
+
+}  // namespace coma
+
+using namespace coma;
+
+extern "C" int coma_roi_paint(const coma_roi_paint_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->roi && a->mri && a->lut && a->roi_ids && a->is_pos && a->pos_prompt && a->neg_prompt && a->out,
+                 "coma_roi_paint: null argument");
+  COMA_CHECK_ARG(a->n_roi > 0 && a->n_roi <= kMaxRoi && a->out_cs >= 3, "coma_roi_paint: n_roi in 1..64, out_cs >= 3");
+  dim3 grid(sweep_blocks(a->V), (unsigned)a->B);
+  if (a->dtype == COMA_BF16) roi_paint_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*a);
+  else roi_paint_kernel<float><<<grid, 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("roi_paint");
+  return COMA_OK;
+}
+
+extern "C" int coma_roi_paint_bwd(const void* dbuf, const float* is_pos, float* dpos, float* dneg, int32_t B, int64_t V,
+                                  int32_t cs, int32_t dtype, coma_stream_t stream) {
+  COMA_CHECK_ARG(dbuf && is_pos && dpos && dneg && B > 0 && V > 0, "coma_roi_paint_bwd: bad arguments");
+  if (dtype == COMA_BF16)
+    roi_paint_bwd_kernel<__nv_bfloat16><<<sweep_blocks(V), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dbuf), is_pos, dpos, dneg, B, V, cs);
+  else
+    roi_paint_bwd_kernel<float><<<sweep_blocks(V), 256, 0, stream>>>(static_cast<const float*>(dbuf), is_pos, dpos, dneg, B, V, cs);
+  COMA_CHECK_LAUNCH("roi_paint_bwd");
+  return COMA_OK;
+}
+
+extern "C" int coma_pack2_fwd(const coma_pack2_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->a && a->b && a->dst && a->dst_cs >= 2, "coma_pack2_fwd: bad arguments");
+  if (a->dtype == COMA_BF16) pack2_kernel<__nv_bfloat16><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
+  else pack2_kernel<float><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("pack2");
+  return COMA_OK;
+}
+
+extern "C" int coma_pack2_bwd(const coma_unpack2_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->ddst && a->dst_cs >= 2, "coma_pack2_bwd: bad arguments");
+  if (a->dtype == COMA_BF16) unpack2_kernel<__nv_bfloat16><<<sweep_blocks(a->V), 256, 0, stream>>>(*a);
+  else unpack2_kernel<float><<<sweep_blocks(a->V), 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("unpack2");
+  return COMA_OK;
+}
+
+extern "C" int coma_roi_mse_chunks(int64_t V) { return mse_chunks(V); }
+
+extern "C" int coma_roi_mse_fwd(const coma_roi_mse_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->pred && a->gt && a->roi && a->roi_ids && a->roi_w && a->partial && a->loss && a->sums,
+                 "coma_roi_mse_fwd: null argument");
+  COMA_CHECK_ARG(a->n_roi > 0 && a->n_roi <= kMaxRoi, "coma_roi_mse_fwd: n_roi in 1..64");
+  const int chunks = mse_chunks(a->V);
+  dim3 grid((unsigned)chunks, (unsigned)a->B);
+  if (a->dtype == COMA_BF16) roi_mse_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*a, chunks);
+  else roi_mse_partial_kernel<float><<<grid, 256, 0, stream>>>(*a, chunks);
+  COMA_CHECK_LAUNCH("roi_mse_partial");
+  roi_mse_finalize_kernel<<<(unsigned)a->B, 32, 0, stream>>>(*a, chunks);
+  COMA_CHECK_LAUNCH("roi_mse_finalize");
+  return COMA_OK;
+}
+
+extern "C" int coma_roi_mse_bwd(const coma_roi_mse_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->pred && a->gt && a->sums && a->dloss && a->dpred, "coma_roi_mse_bwd: null argument");
+  dim3 grid(sweep_blocks(a->V), (unsigned)a->B);
+  if (a->dtype == COMA_BF16) roi_mse_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*a);
+  else roi_mse_bwd_kernel<float><<<grid, 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("roi_mse_bwd");
+  return COMA_OK;
+}

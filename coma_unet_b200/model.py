@@ -1,0 +1,306 @@
+"""Drop-in model classes: same names, constructor signatures, forward contract and ``state_dict`` keys
+as the reference's attn_unet_data_parallel.py:120-693, executing on hand-written sm_100a kernels.
+
+* ``UpBlock`` (:120-131), ``ObservableAttentionBlock`` (:134-150), ``AttentionLayer`` (:152-240),
+  ``ObservableAttentionUnet`` (:243-432), ``ProjectionHead`` (:436-454),
+  ``StackedFusionConvLayers`` (:480-501), ``ContrastiveAttentionUNET_DP`` (:503-693).
+
+User-facing tensors keep the reference's ``[B, C, D, H, W]`` shapes; internally activations are NDHWC
+in ``compute_dtype`` (bf16 by default, ``compute_dtype=torch.float32`` for the exact-fp32 path).
+Two constructor extensions ride on the reference's ``**kwargs`` (:520): ``prompt_shape`` (default
+``(128,128,128)``, the reference's hard-coded prompt size) and ``compute_dtype``.
+
+Behavioural notes: the reference runs its backbone twice per forward and discards the
+first result (:664,666); here it runs once and BatchNorm running statistics receive the equivalent
+double update.  The B x 36 masked ``index_put_`` / ``.item()`` loop (:637-647) is one kernel.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import blocks, cond_conv, ops
+
+ROI_INDICES = [
+    1001, 1006, 1007, 1009, 1015, 1016, 1030, 1034, 1033, 1008, 1025, 1029, 1031, 1022, 17, 18,
+    2001, 2006, 2007, 2009, 2015, 2016, 2030, 2034, 2033, 2008, 2025, 2029, 2031, 2022, 49, 50, 51, 52, 53, 54,
+]
+_CTX = ["bankssts", "entorhinal", "fusiform", "inferiortemporal", "middletemporal", "parahippocampal",
+        "superiortemporal", "transversetemporal", "temporalpole", "inferiorparietal", "precuneus",
+        "superiorparietal", "supramarginal", "postcentral"]
+ROI_NAMES = ([f"ctx-lh-{n}" for n in _CTX] + ["Left-Hippocampus", "Left-Amygdala"] + [f"ctx-rh-{n}" for n in _CTX]
+             + ["Right-Thalamus-Proper", "Right-Caudate", "Right-Putamen", "Right-Pallidum", "Right-Hippocampus",
+                "Right-Amygdala"])
+
+
+def save_attention_coeffs(path: str, coeff: torch.Tensor) -> None:
+    """Stand-in for data_util.save_attention_coeffs (data_util.py:802-811): ``<stem>_vdim<W>.npy``."""
+    vol = np.squeeze(coeff.detach().float().cpu().numpy())
+    stem = path.rsplit(".", 1)[0] if "." in path else path
+    np.save(f"{stem}_vdim{vol.shape[-1]}.npy", vol)
+
+
+class UpBlock(blocks.UpConv):
+    def __init__(self, conditional, num_covars=0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if conditional:
+            self.up = cond_conv.CondConvolution(dropout=0.0, is_transposed=True, num_covars=num_covars, *args, **kwargs)
+        self.conditional = conditional
+
+    def forward(self, x, covariate=None, out=None):
+        return self.up(x, covariate, out=out) if self.conditional else self.up(x, out=out)
+
+
+class ObservableAttentionBlock(blocks.AttentionBlock):
+    save_attn = None
+
+    def forward(self, g, x, out=None):
+        return super().forward(g, x, out=out, want_coeff=bool(self.save_attn))
+
+
+class AttentionLayer(blocks.AttentionLayer):
+    save_attn = None
+
+    def __init__(self, spatial_dims, in_channels, out_channels, submodule, up_kernel_size=3, strides=2, dropout=0.0,
+                 conditional=False, num_covars=0):
+        super().__init__(spatial_dims, in_channels, out_channels, submodule, up_kernel_size, strides, dropout)
+        self.attention = ObservableAttentionBlock(spatial_dims, f_g=in_channels, f_l=in_channels, f_int=in_channels // 2)
+        self.upconv = UpBlock(conditional=conditional, spatial_dims=spatial_dims, in_channels=out_channels,
+                              out_channels=in_channels, strides=strides, kernel_size=up_kernel_size,
+                              num_covars=num_covars)
+
+    def set_save_attn(self, status):
+        self.save_attn = status
+        self.attention.save_attn = status
+
+    def forward(self, x, covariate=None):
+        """-> (decoder output, encoder tensors from this level down, decoder tensors from this level down)."""
+        cov5 = covariate[:, :, :5] if covariate is not None else None
+        if isinstance(self.submodule, nn.Sequential):
+            block, deeper = self.submodule[0], self.submodule[1]
+            x_sub, encs, decs = deeper(block(x, covariate=cov5), covariate=covariate)
+        else:
+            x_sub = self.submodule(x, covariate=cov5)
+            encs, decs = [x_sub], []
+        Cn = x.shape[-1]
+        grad = torch.is_grad_enabled() and (x.requires_grad or x_sub.requires_grad or self.merge.conv.weight.requires_grad)
+        if not grad:
+            # one concat buffer written in place: [att | fromlower]  (replaces torch.cat, :229)
+            cat = x.new_empty(*x.shape[:-1], 2 * Cn)
+            fromlower = self.upconv(x_sub, covariate, out=cat[..., Cn:])
+            att = self.attention(g=fromlower, x=x, out=cat[..., :Cn])
+        else:
+            fromlower = self.upconv(x_sub, covariate)
+            att = self.attention(g=fromlower, x=x)
+        if self.save_attn is not None:
+            att, coeff = att
+            save_attention_coeffs(self.save_attn, coeff)
+        if grad:
+            cat = ops.concat2(att, fromlower)
+        att_m = self.merge(cat)
+        return att_m, [x] + encs, [att_m] + decs
+
+
+class _PlainBlock(blocks.ConvBlock):
+    def __init__(self, num_covars=0, **kw):
+        super().__init__(**kw)
+
+    def forward(self, x, covariate=None):
+        return super().forward(x)
+
+
+class _PlainConvolution(blocks.Convolution):
+    def __init__(self, *a, num_experts=1, num_covars=0, **kw):
+        super().__init__(*a, **kw)
+
+    def forward(self, x, covariate=None, out=None):
+        return super().forward(x, out=out)
+
+
+class ObservableAttentionUnet(nn.Module):
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, channels: Sequence[int],
+                 strides: Sequence[int], kernel_size=3, up_kernel_size=3, dropout: float = 0.0,
+                 conditional: bool = False):
+        super().__init__()
+        self.dimensions, self.in_channels, self.out_channels = spatial_dims, in_channels, out_channels
+        self.channels, self.strides, self.kernel_size = channels, strides, kernel_size
+        self.dropout, self.conditional, self.up_kernel_size = dropout, conditional, up_kernel_size
+        self.with_regression = True
+        self.save_attn = None
+        self.compute_dtype = torch.bfloat16
+        Block = cond_conv.CondConvBlock if conditional else _PlainBlock
+        Conv = cond_conv.CondConvolution if conditional else _PlainConvolution
+        ncov_up = 5 + int(self.with_regression)
+        head = Block(spatial_dims=spatial_dims, in_channels=in_channels, out_channels=channels[0], dropout=dropout,
+                     num_covars=5)
+        reduce_channels = Conv(spatial_dims=spatial_dims, in_channels=channels[0], out_channels=out_channels,
+                               kernel_size=1, strides=1, padding=0, conv_only=True, num_experts=8, num_covars=ncov_up)
+
+        def level(ch, st):
+            down = Block(spatial_dims=spatial_dims, in_channels=ch[0], out_channels=ch[1], strides=st[0],
+                         dropout=dropout, num_covars=5)
+            sub = nn.Sequential(down, level(ch[1:], st[1:])) if len(ch) > 2 else down
+            return AttentionLayer(spatial_dims=spatial_dims, in_channels=ch[0], out_channels=ch[1], submodule=sub,
+                                  up_kernel_size=up_kernel_size, strides=st[0], dropout=dropout,
+                                  conditional=conditional, num_covars=ncov_up)
+
+        self.model = nn.ModuleList([head, level(list(channels), list(strides)), reduce_channels])
+
+    def set_save_attn(self, value):
+        layer = self.model[1]
+        while isinstance(layer, AttentionLayer):
+            layer.set_save_attn(value)
+            sub = layer.submodule
+            if not isinstance(sub, nn.Sequential):
+                break
+            layer = sub[-1]
+
+    def set_compute_dtype(self, dtype):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.compute_dtype = dtype
+        return self
+
+    def _backbone(self, xv, covariate):
+        """NDHWC in, NDHWC out: (x[B,D,H,W,out], encoder tensors, decoder tensors)."""
+        head, encdec, reduce_channels = self.model
+        h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
+        d, encs, decs = encdec(h, covariate)
+        return reduce_channels(d, covariate=covariate), encs, decs
+
+    def forward(self, x, covariate=None):
+        xv = ops.ncdhw_to_vol(x, self.compute_dtype)
+        out, encs, decs = self._backbone(xv, covariate)
+        to_user = lambda t: ops.vol_to_ncdhw(t).float()   # noqa: E731
+        return to_user(out), [to_user(e) for e in encs], [to_user(d) for d in decs]
+
+
+class ProjectionHead(nn.Module):
+    def __init__(self, in_channels, out_channels, latent_space_dim, kernel_size=3):
+        super().__init__()
+        self.conv = blocks.ConvBlock(3, in_channels, 1, kernel_size=1)
+        self.act_fn = nn.ReLU()
+
+    def forward(self, x):
+        """x: NDHWC encoder tensor -> [B, voxels] fp32 (the trailing ReLU is a no-op after ConvBlock's ReLU)."""
+        y = self.conv(x)
+        return y.reshape(y.shape[0], -1).float()
+
+
+class StackedFusionConvLayers(nn.Module):
+    def __init__(self, input_feature_channels, bottleneck_feature_channel, output_feature_channels, num_convs,
+                 nonlin=nn.LeakyReLU, nonlin_kwargs=None):
+        super().__init__()
+        self.input_channels, self.output_channels = input_feature_channels, output_feature_channels
+        act = (nonlin, nonlin_kwargs or {"negative_slope": 1e-2, "inplace": True})
+        widths = [input_feature_channels] + [bottleneck_feature_channel] * (num_convs - 1) + [output_feature_channels]
+        # intermediate tensors keep 16 channels (zero padded) so every conv is tcgen05-shaped
+        self.blocks = nn.Sequential(*[
+            blocks.Convolution(3, widths[i], widths[i + 1], act=act, pad_out=16 if i < num_convs - 1 else 1)
+            for i in range(num_convs)])
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
+    PAD = 16   # channel padding of the small modulator tensors
+
+    def __init__(self, spatial_dims, in_channels, out_channels, channels, strides, latent_spaces, kernel_size=3,
+                 up_kernel_size=3, dropout=0, training=True, embeddings_out=False, conditional=False,
+                 decoder_ds=False, **kwargs):
+        super().__init__(spatial_dims, in_channels, out_channels, channels, strides, kernel_size, up_kernel_size,
+                         dropout, conditional)
+        self.training = training
+        self.embeddings_out, self.decoder_ds = embeddings_out, decoder_ds
+        self.depth = len(channels)
+        ps = tuple(kwargs.get("prompt_shape", (128, 128, 128)))
+        self.compute_dtype = kwargs.get("compute_dtype", torch.bfloat16)
+
+        self.projection_heads = nn.ModuleList([
+            ProjectionHead(channels[i], int((128 / 2 ** i) ** 3), latent_spaces[i]) for i in range(len(channels))])
+        self.final_projection_head = nn.Sequential(nn.AdaptiveAvgPool3d(1), nn.Linear(out_channels, latent_spaces[-1]),
+                                                   nn.ReLU())
+        self.pos_dynamic_prompt = nn.Parameter(torch.randn(1, 1, *ps))
+        self.neg_dynamic_prompt = nn.Parameter(torch.randn(1, 1, *ps))
+        self.fusion_layer = StackedFusionConvLayers(2, 8, 1, num_convs=3)
+        self.modulator = blocks.Convolution(3, 2, 1, act="ReLU")        # unused in forward (reference :547)
+        self.modulator_3c = blocks.Convolution(3, 3, 1, act="ReLU")     # unused in forward (reference :548)
+        self.reweigh = nn.Parameter(torch.ones(ps))                      # unused in forward
+        self.final_act = nn.ReLU()
+        self.pos_reweigh = nn.Parameter(torch.ones((1, *ps)))            # unused in forward
+        self.neg_reweigh = nn.Parameter(torch.ones((1, *ps)))            # unused in forward
+        self.deep_modulator_3c = StackedFusionConvLayers(3, 16, 1, num_convs=3)
+        self.final_pred_head = blocks.Convolution(3, 2, 1, kernel_size=1)
+
+        self.roi_indices = list(ROI_INDICES)
+        self.roi_names = list(ROI_NAMES)
+        self.roi_ind_names_dict = dict(zip(ROI_INDICES, ROI_NAMES))
+        self.roi_ind_vol_names_dict = {k: "vol_" + "_".join(v.split("-")) for k, v in self.roi_ind_names_dict.items()}
+        self.general_dynamic_prompt = nn.Parameter(torch.randn(1, 1, *ps))
+        self.roi_wise_reweigh = nn.ParameterList([nn.Parameter(torch.ones(1)) for _ in ROI_INDICES])  # unused
+        self.all_stages, self.only_stage_two = True, False
+        self.with_uq = kwargs.get("with_uq", False)
+        self._roi_ids = None
+
+    def set_training(self, mode):
+        self.training = mode
+
+    def get_depth(self):
+        return self.depth
+
+    # -- ROI lookup table: host dicts -> one small pinned upload, no per-ROI device work ---------------
+    def _roi_lut(self, roi_pred_dicts, device):
+        B = len(roi_pred_dicts)
+        lut = np.empty((B, len(self.roi_indices), 2), dtype=np.float32)
+        for b, d in enumerate(roi_pred_dicts):
+            for i, idx in enumerate(self.roi_indices):
+                entry = d[self.roi_ind_names_dict[idx]]
+                lut[b, i, 0] = np.nan_to_num(entry["loc"])
+                lut[b, i, 1] = np.nan_to_num(entry["std"])
+        t = torch.from_numpy(lut)
+        if device.type == "cuda":
+            t = t.pin_memory().to(device, non_blocking=True)
+        if self._roi_ids is None or self._roi_ids.device != device:
+            self._roi_ids = torch.tensor(self.roi_indices, dtype=torch.int32, device=device)
+        return t
+
+    def forward_modulator_with_uq(self, x, out, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
+        """x: user input [B,1,D,H,W] fp32; out: backbone output NDHWC [B,D,H,W,1].  Returns NDHWC [B,D,H,W,1]."""
+        dev, dt = out.device, out.dtype
+        B = x.shape[0]
+        lut = self._roi_lut(roi_pred_dicts, dev)
+        cov0 = covariate.reshape(B, -1)[:, 0]
+        is_pos = (cov0 == 1).to(device=dev, dtype=torch.float32)
+        used = (True, True)
+        if torch.is_grad_enabled() and (self.pos_dynamic_prompt.requires_grad or self.neg_dynamic_prompt.requires_grad):
+            flags = (cov0 == 1).cpu()      # which prompts get a gradient at all (None otherwise, like the reference)
+            used = (bool(flags.any()), bool((~flags).any()))
+        painted = ops.RoiPaintFn.apply(self.pos_dynamic_prompt, self.neg_dynamic_prompt, sample_roi_mask, x, lut,
+                                       self._roi_ids, is_pos, self.PAD, dt, used)
+        m1 = self.deep_modulator_3c(painted)                                           # [B,D,H,W,1]
+        packed = ops.Pack2Fn.apply(m1, self.general_dynamic_prompt, out, self.PAD)     # [general + m1 | out | 0..]
+        fused = self.fusion_layer(packed)                                              # [B,D,H,W,1]
+        pair = ops.Pack2Fn.apply(out, None, fused, 2)                                  # [out | fused]
+        return self.final_pred_head(pair, final_relu=True)                             # conv1x1 + IN + PReLU, then ReLU
+
+    def forward(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
+        if covariate is not None and x.device != covariate.device:
+            covariate = covariate.to(x.device)
+        xv = ops.ncdhw_to_vol(x, self.compute_dtype)
+        with blocks.bn_updates(2):   # the reference's duplicated backbone pass (:664,666) in closed form
+            out, encoder_extractions, _ = self._backbone(xv, covariate)
+        out = self.forward_modulator_with_uq(x, out, covariate, roi_pred_dicts, sample_roi_mask)
+        pred = ops.vol_to_ncdhw(out).float()
+        if not self.training and not self.embeddings_out:
+            return pred
+        projected = [self.projection_heads[i](encoder_extractions[i]) for i in range(self.depth)]
+        final_proj = self.final_projection_head(pred)
+        if self.embeddings_out:
+            return pred, projected, final_proj, [ops.vol_to_ncdhw(e).float() for e in encoder_extractions]
+        if self.decoder_ds:
+            return pred, projected, final_proj, []
+        return pred, projected, final_proj

