@@ -1,6 +1,7 @@
 // C-ABI entry points that dispatch between kernel implementations (include/coma_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,10 +43,19 @@ static int check_conv(const coma_conv_args* a, const char* who) {
   return COMA_OK;
 }
 
+// COMA_DISABLE_TCGEN05=1 routes IMPL_AUTO to the CUDA-core kernels (A/B debugging of the tensor-core path)
+static bool tc_enabled() {
+  static const bool on = [] { const char* e = getenv("COMA_DISABLE_TCGEN05"); return !(e && e[0] == '1'); }();
+  return on;
+}
+static int pick_impl(const coma_conv_args& a) {
+  if (a.impl != COMA_IMPL_AUTO) return a.impl;
+  return (tc_enabled() && conv_tc_supported(a)) ? COMA_IMPL_TCGEN05 : COMA_IMPL_SIMT;
+}
+
 static int run_conv(const coma_conv_args* a, cudaStream_t stream, const char* who) {
   if (int rc = check_conv(a, who)) return rc;
-  int impl = a->impl;
-  if (impl == COMA_IMPL_AUTO) impl = conv_tc_supported(*a) ? COMA_IMPL_TCGEN05 : COMA_IMPL_SIMT;
+  const int impl = pick_impl(*a);
   if (impl == COMA_IMPL_TCGEN05) {
     if (!conv_tc_supported(*a)) {
       set_error("%s: problem not supported by the tcgen05 path", who);
@@ -65,8 +75,7 @@ extern "C" const char* coma_last_error(void) { return g_error; }
 
 extern "C" int coma_conv3d_stat_chunks(const coma_conv_args* a) {
   if (!a) return 0;
-  int impl = a->impl;
-  if (impl == COMA_IMPL_AUTO) impl = conv_tc_supported(*a) ? COMA_IMPL_TCGEN05 : COMA_IMPL_SIMT;
+  const int impl = pick_impl(*a);
   return impl == COMA_IMPL_TCGEN05 ? conv_tc_stat_chunks(*a) : conv_simt_stat_chunks(*a);
 }
 extern "C" int coma_conv3d_tcgen05_supported(const coma_conv_args* a) { return a && conv_tc_supported(*a) ? 1 : 0; }

@@ -1,7 +1,468 @@
-// placeholder until the tcgen05 kernel lands
+// 3-D convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, tiled 5-D boxes with hardware zero-fill for the halo)  ->  128B/64B/32B-swizzled
+//   shared memory  ->  tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM)  ->  tcgen05.ld epilogue.
+//
+// Replaces cuDNN fprop/dgrad behind torch.nn.Conv3d / ConvTranspose3d on the reference's hot path
+// (attn_unet_data_parallel.py:126,285-306,495-497; MONAI ConvBlock / UpConv / AttentionLayer.merge).
+//
+// GEMM view: M = 128 output voxels (an 8 x 4 x 4 box in W,H,D), N = Cout tile (<= 256), K = taps x Cin.
+// One k-step = one filter tap x one channel chunk KC (16/32/64): the A operand is the activation box shifted
+// by the tap (a fresh TMA load; out-of-bounds voxels arrive as zeros = the conv padding), the B operand is the
+// [Cout x KC] slice of the packed weights w[tap][Cout][Cin].  Stride-2 convolutions use the TMA element stride.
+// The transposed convolution (k3, s2, p1, op1) runs as 8 output-parity classes, each an ordinary stride-1
+// gather over the INPUT grid with 1..8 taps, scattered to the strided output positions by the epilogue.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer +
+// TMEM allocator, warps 2..5 = epilogue (bias, per-channel statistics partials, per-(sample,channel) affine,
+// activation, bf16 store).  Two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
 #include "common.cuh"
+
 namespace coma {
-bool conv_tc_supported(const coma_conv_args&) { return false; }
-int conv_tc_stat_chunks(const coma_conv_args&) { return 0; }
-int conv_tc_launch(const coma_conv_args&, cudaStream_t) { set_error("tcgen05 path not built"); return COMA_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TW = 8, TH = 4, TD = 4;      // M tile = 128 voxels
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+  int B, Di, Hi, Wi, Do, Ho, Wo, Cin, Cout;
+  int ksize, stride, pad, transposed;
+  int KC, kchunks, NT, n_tiles;
+  int tiles_w, tiles_h, tiles_d, classes, total_tiles;
+  int stages;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  int swz;                  // swizzle span in bytes: 32 / 64 / 128
+  __nv_bfloat16* y;
+  int y_cs, y_cn;
+  const float* bias; const float* scale; const float* shift; const float* slope;
+  float* stats;
+  int act, stat_chunks;
+  uint32_t tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();   // watchdog: a lost TMA / MMA completion must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of `swz` bytes, 8-row groups
+// `8*swz` bytes apart (SBO), version 1 (sm_100), layout = 2 (128B) / 4 (64B) / 6 (32B swizzle).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
+  const uint64_t layout = swz == 128 ? 2ull : (swz == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                           // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((8u * (uint32_t)swz) >> 4) << 32;  // SBO
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+// taps of a tile: ordinary conv -> all k^3 taps; transposed conv -> the taps that hit output parity class `cls`
+struct Tap { int dd, dh, dw, widx; };
+__device__ __forceinline__ int num_taps(const TcParams& p, int cls) {
+  if (!p.transposed) return p.ksize * p.ksize * p.ksize;
+  return (1 + (cls & 1)) * (1 + ((cls >> 1) & 1)) * (1 + ((cls >> 2) & 1));
+}
+__device__ __forceinline__ Tap get_tap(const TcParams& p, int cls, int t) {
+  Tap r;
+  if (!p.transposed) {
+    const int K = p.ksize;
+    const int kw = t % K, kh = (t / K) % K, kd = t / (K * K);
+    r.dw = kw - p.pad; r.dh = kh - p.pad; r.dd = kd - p.pad; r.widx = t;
+    return r;
+  }
+  // per dim: parity 0 -> (k=1, shift 0); parity 1 -> (k=0, shift +1), (k=2, shift 0)        [o = 2*i - 1 + k]
+  const int pw = cls & 1, ph = (cls >> 1) & 1, pd = (cls >> 2) & 1;
+  const int nw = 1 + pw, nh = 1 + ph;
+  const int iw = t % nw, ih = (t / nw) % nh, id = t / (nw * nh);
+  const int kw = pw ? (iw ? 2 : 0) : 1, kh = ph ? (ih ? 2 : 0) : 1, kd = pd ? (id ? 2 : 0) : 1;
+  r.dw = (pw && !iw) ? 1 : 0; r.dh = (ph && !ih) ? 1 : 0; r.dd = (pd && !id) ? 1 : 0;
+  r.widx = (kd * 3 + kh) * 3 + kw;
+  return r;
+}
+
+struct TileCoord { int n_tile, cls, b, d0, h0, w0; };
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord c;
+  c.n_tile = t % p.n_tiles; t /= p.n_tiles;
+  c.w0 = (t % p.tiles_w) * TW; t /= p.tiles_w;
+  c.h0 = (t % p.tiles_h) * TH; t /= p.tiles_h;
+  c.d0 = (t % p.tiles_d) * TD; t /= p.tiles_d;
+  c.cls = t % p.classes; t /= p.classes;
+  c.b = t;
+  return c;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][NT][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int nt = num_taps(p, tc.cls);
+        const int es = p.transposed ? 1 : p.stride;
+        for (int tap = 0; tap < nt; ++tap) {
+          const Tap tp = get_tap(p, tc.cls, tap);
+          const int cw = tc.w0 * es + tp.dw, ch = tc.h0 * es + tp.dh, cd = tc.d0 * es + tp.dd;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* b_dst = a_dst + p.a_bytes;
+            mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+            tma_load_5d(a_dst, &tmA, &full[stage], kc * p.KC, cw, ch, cd, tc.b);
+            tma_load_2d(b_dst, &tmB, &full[stage], kc * p.KC, tp.widx * p.Cout + tc.n_tile * p.NT);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+        const TileCoord tc = decode_tile(p, t);
+        const int ksteps = num_taps(p, tc.cls) * p.kchunks;
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          const uint64_t adesc = make_desc(a_addr, p.swz), bdesc = make_desc(b_addr, p.swz);
+          const int kk_n = p.KC >> 4;
+          for (int kk = 0; kk < kk_n; ++kk) {
+            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ks | kk) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);              // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) =========================
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;           // GEMM row = voxel inside the tile
+    const int lw = row % TW, lh = (row / TW) % TH, ld = row / (TW * TH);
+    const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    float* wstat = sstat + (size_t)(warp - 2) * p.NT * 2;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+      const TileCoord tc = decode_tile(p, t);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      // output voxel of this row
+      int od, oh, ow;
+      bool valid;
+      if (!p.transposed) {
+        od = tc.d0 + ld; oh = tc.h0 + lh; ow = tc.w0 + lw;
+        valid = od < p.Do && oh < p.Ho && ow < p.Wo;
+      } else {
+        const int id = tc.d0 + ld, ih = tc.h0 + lh, iw = tc.w0 + lw;
+        valid = id < p.Di && ih < p.Hi && iw < p.Wi;
+        od = 2 * id + ((tc.cls >> 2) & 1); oh = 2 * ih + ((tc.cls >> 1) & 1); ow = 2 * iw + (tc.cls & 1);
+      }
+      const int n0 = tc.n_tile * p.NT;
+      __nv_bfloat16* yrow = p.y + ((((int64_t)tc.b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.y_cs + n0;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.NT; c0 += 16) {
+        uint32_t raw[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + c0), raw);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+          if (!valid) v[j] = 0.f;
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s1 = warp_sum(v[j]), s2 = warp_sum(v[j] * v[j]);
+            if (lane == 0) { wstat[(c0 + j) * 2] = s1; wstat[(c0 + j) * 2 + 1] = s2; }
+          }
+        }
+        if (valid) {
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[j] = fmaf(__ldg(p.scale + (int64_t)tc.b * p.Cout + n0 + c0 + j), v[j], __ldg(p.shift + (int64_t)tc.b * p.Cout + n0 + c0 + j));
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
+          if (n0 + c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+            hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
+            reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      // accumulator drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // chunk index of this tile inside its sample
+        int tt = t / p.n_tiles;
+        const int per_sample = p.tiles_w * p.tiles_h * p.tiles_d * p.classes;
+        const int chunk = tt % per_sample;
+        for (int i = threadIdx.x - 64; i < p.NT * 2; i += 128) {
+          const float s = sstat[i] + sstat[p.NT * 2 + i] + sstat[p.NT * 4 + i] + sstat[p.NT * 6 + i];
+          p.stats[(((int64_t)tc.b * p.stat_chunks + chunk) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = s;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+std::mutex g_map_mutex;
+std::unordered_map<std::string, CUtensorMap> g_map_cache;
+
+bool make_map(CUtensorMap* out, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box, const cuuint32_t* estr, int swz) {
+  std::string key(reinterpret_cast<const char*>(&base), sizeof(base));
+  key.append(reinterpret_cast<const char*>(dims), sizeof(cuuint64_t) * rank);
+  key.append(reinterpret_cast<const char*>(strides_bytes), sizeof(cuuint64_t) * (rank - 1));
+  key.append(reinterpret_cast<const char*>(box), sizeof(cuuint32_t) * rank);
+  key.append(reinterpret_cast<const char*>(estr), sizeof(cuuint32_t) * rank);
+  key.push_back((char)swz);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return false; }
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return false; }
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache.emplace(key, *out);
+  return true;
+}
+
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin == 32 ? 32 : (cin == 16 ? 16 : 0)); }
+int pick_nt(int cout) {
+  if (cout <= 256) return cout;
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (cout % nt == 0) return nt;
+  return 0;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const coma_conv_args& a) {
+  if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
+  if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;
+  if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return false;
+  if (a.transposed) return a.ksize == 3 && a.stride == 2;
+  return (a.ksize == 1 || a.ksize == 3) && (a.stride == 1 || a.stride == 2);
+}
+
+static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int& classes) {
+  const int gw = a.transposed ? a.Wi : a.Wo, gh = a.transposed ? a.Hi : a.Ho, gd = a.transposed ? a.Di : a.Do;
+  tw = (gw + TW - 1) / TW; th = (gh + TH - 1) / TH; td = (gd + TD - 1) / TD;
+  classes = a.transposed ? 8 : 1;
+}
+
+int conv_tc_stat_chunks(const coma_conv_args& a) {
+  int tw, th, td, cl;
+  tile_counts(a, tw, th, td, cl);
+  return tw * th * td * cl;
+}
+
+int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
+  TcParams p{};
+  p.B = a.B; p.Di = a.Di; p.Hi = a.Hi; p.Wi = a.Wi; p.Do = a.Do; p.Ho = a.Ho; p.Wo = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout;
+  p.ksize = a.ksize; p.stride = a.stride; p.pad = a.pad; p.transposed = a.transposed;
+  p.KC = pick_kc(a.Cin); p.kchunks = a.Cin / p.KC;
+  p.NT = pick_nt(a.Cout); p.n_tiles = a.Cout / p.NT;
+  tile_counts(a, p.tiles_w, p.tiles_h, p.tiles_d, p.classes);
+  p.total_tiles = a.B * p.classes * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
+  p.swz = p.KC * 2;
+  p.a_bytes = 128u * p.KC * 2u;
+  p.b_bytes = (uint32_t)p.NT * p.KC * 2u;
+  p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+  p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
+  p.stat_chunks = p.tiles_w * p.tiles_h * p.tiles_d * p.classes;
+  uint32_t cols = 32;
+  while (cols < 2u * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+
+  const size_t tail = 2 * kMaxStages * 8 + 4 * 8 + 16 + (size_t)4 * p.NT * 2 * sizeof(float) + 64;
+  const size_t budget = 200 * 1024;
+  int stages = (int)((budget - tail - 1024) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { set_error("conv_tc: stage of %u bytes does not fit", p.stage_bytes); return COMA_ERR_UNSUPPORTED; }
+  p.stages = stages;
+  const size_t smem_bytes = 1024 + (size_t)stages * p.stage_bytes + tail;
+
+  // A: activations [B, D, H, W, C] (innermost first for TMA), element stride = conv stride on the spatial dims
+  CUtensorMap tmA, tmB;
+  {
+    const int es = a.transposed ? 1 : a.stride;
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
+                             (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)(TW * es), (cuuint32_t)(TH * es), (cuuint32_t)(TD * es), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, (cuuint32_t)es, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
+    if (!make_map(&tmA, base, 5, dims, strides, box, estr, p.swz)) return COMA_ERR_CUDA;
+  }
+  {
+    const int taps = a.ksize * a.ksize * a.ksize;
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)taps * a.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.NT};
+    cuuint32_t estr[2] = {1, 1};
+    if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, p.swz)) return COMA_ERR_CUDA;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = num_sms();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  conv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  COMA_CHECK_LAUNCH("conv_tc");
+  return COMA_OK;
+}
+
+}  // namespace coma

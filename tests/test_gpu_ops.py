@@ -324,3 +324,57 @@ def test_roi_paint_pack_and_mse(dtype):
     (lp * coef).sum().backward()
     assert err(pp.grad.float(), pr.grad) < TOL[dtype]
     assert err(cu.RoiMSE(w, common.ROI_INDICES, voxel_wise=False)(pp.detach(), tau, roi), ocrit.RoiMSE(w, common.ROI_INDICES, voxel_wise=False)(pr.detach(), tau, roi)) < 1e-4
+
+
+TC_CASES = [
+    # (B, Cin, Cout, D, H, W, k, stride, transposed)
+    (2, 32, 32, 16, 16, 16, 3, 1, False),
+    (1, 64, 32, 12, 9, 20, 3, 1, False),     # ragged tiles, K chunk 64 (128B swizzle)
+    (1, 16, 16, 8, 8, 8, 3, 1, False),       # 32B swizzle
+    (2, 128, 64, 8, 8, 8, 3, 1, False),      # two K chunks per tap
+    (1, 64, 512, 4, 4, 8, 3, 1, False),      # two N tiles
+    (2, 32, 64, 16, 16, 16, 3, 2, False),    # TMA element stride 2
+    (1, 64, 128, 10, 6, 12, 3, 2, False),
+    (2, 64, 32, 8, 8, 8, 3, 2, True),        # transposed: 8 parity classes
+    (1, 32, 16, 5, 3, 6, 3, 2, True),
+    (2, 64, 32, 8, 8, 8, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tcgen05_conv_matches_cuda_core_conv(case):
+    """The tensor-core implicit GEMM, forced, against the exact direct conv on the same bf16 data (and torch)."""
+    B, Cin, Cout, D, H, W, k, s, tr = case
+    dtype = torch.bfloat16
+    x = rnd(B, Cin, D, H, W, seed=60).bfloat16().float()
+    wshape = (Cin, Cout, k, k, k) if tr else (Cout, Cin, k, k, k)
+    w = rnd(*wshape, seed=61, scale=(Cin * k ** 3) ** -0.5).bfloat16().float()
+    b = rnd(Cout, seed=62, scale=0.1)
+    scale, shift = (1 + 0.2 * rnd(B, Cout, seed=63)).contiguous(), (0.1 * rnd(B, Cout, seed=64)).contiguous()
+    pad = (k - 1) // 2
+    ref = F.conv_transpose3d(x, w, b, stride=s, padding=pad, output_padding=s - 1) if tr else F.conv3d(x, w, b, stride=s, padding=pad)
+    wp = ops.pack_weight(w, tr, Cin, Cout, dtype)
+    xv = to_vol(x, dtype)
+    outs = {}
+    for impl in (L.IMPL_TCGEN05, L.IMPL_SIMT):
+        y, st = ops.conv_raw(xv, wp, b, ksize=k, stride=s, transposed=tr, want_stats=True, impl=impl)
+        ye, _ = ops.conv_raw(xv, wp, b, ksize=k, stride=s, transposed=tr, scale=scale, shift=shift, act=L.ACT_RELU, impl=impl)
+        outs[impl] = (y.float(), st.sum(dim=1), ye.float())
+    yt, st_t, yet = outs[L.IMPL_TCGEN05]
+    ys, st_s, yes = outs[L.IMPL_SIMT]
+    assert err(to_ncdhw(yt), ref) < 1e-2
+    assert err(yt, ys) < 1e-2 and err(yet, yes) < 1e-2
+    assert err(st_t, st_s) < 1e-3
+    refe = torch.relu(ref * scale[:, :, None, None, None] + shift[:, :, None, None, None])
+    assert err(to_ncdhw(yet), refe) < 1e-2
+
+
+def test_tcgen05_is_selected_for_hot_path_shapes():
+    import ctypes
+    x = torch.zeros(1, 8, 8, 8, 32, device=DEV, dtype=torch.bfloat16)
+    wp = torch.zeros(27, 32, 32, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(1, 8, 8, 8, 32, device=DEV, dtype=torch.bfloat16)
+    a = ops._conv_args(x, wp, None, y, ksize=3, stride=1, transposed=False, cout_comp=32)
+    assert L.lib().coma_conv3d_tcgen05_supported(ctypes.byref(a)) == 1
+    a32 = ops._conv_args(x.float(), wp.float(), None, y.float(), ksize=3, stride=1, transposed=False, cout_comp=32)
+    assert L.lib().coma_conv3d_tcgen05_supported(ctypes.byref(a32)) == 0
