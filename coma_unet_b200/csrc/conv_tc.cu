@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -332,6 +333,250 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// ================================================================================================
+// v2: halo-reuse kernel for 3x3x3 stride-1 convolutions with few channels (Cin, Cout <= 64).
+//
+// The per-tap kernel above re-reads every activation tile 27x from L2 and pays one TMA + two mbarrier round
+// trips per tap; at 128^3 with 16..64 channels that, not the tensor core, sets the time.  Here a CTA sweeps a
+// column of the volume plane by plane: M tile = 8(w) x 16(h) voxels of one d-plane, each input plane is loaded ONCE
+// as a 10 x 18 halo slab (one TMA box, zero-filled outside the volume), kept in a ring of shared-memory slots,
+// and used by all 27 taps of three consecutive output planes through shifted UMMA descriptors
+// (start = slab + (kh*10 + kw) rows, 8-row groups 10 rows apart).  tcgen05 applies the 128B/64B/32B swizzle to
+// absolute shared-memory address bits, so such unaligned starts read exactly what TMA wrote
+// (profiles/r01_probe_umma_descriptor_addressing.log).  All 27 weight tiles stay resident in shared memory.
+// ================================================================================================
+constexpr int HW_T = 8, HH_T = 16, HALO_W = HW_T + 2, HALO_H = HH_T + 2, HALO_ROWS = HALO_W * HALO_H;
+constexpr int kMaxSlabs = 8;
+
+struct HaloParams {
+  int B, D, H, W, Cin, Cout;
+  int KC;
+  int cols_w, cols_h, segs_d, DS, total_segs;
+  int nslab;
+  uint32_t rowb, slab_bytes, slab_tx, w_tile_bytes, w_bytes;
+  __nv_bfloat16* y;
+  int y_cs, y_cn;
+  const float* bias; const float* scale; const float* shift; const float* slope;
+  float* stats;
+  int act, stat_chunks;
+  uint32_t tmem_cols;
+};
+
+struct SegCoord { int b, d0, nd, h0, w0, chunk; };
+__device__ __forceinline__ SegCoord decode_seg(const HaloParams& p, int t) {
+  SegCoord c;
+  const int per_sample = p.cols_w * p.cols_h * p.segs_d;
+  c.b = t / per_sample;
+  c.chunk = t % per_sample;
+  int r = c.chunk;
+  c.w0 = (r % p.cols_w) * HW_T; r /= p.cols_w;
+  c.h0 = (r % p.cols_h) * HH_T; r /= p.cols_h;
+  c.d0 = r * p.DS;
+  c.nd = min(p.DS, p.D - c.d0);
+  return c;
+}
+
+template <int NT, int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;                                                   // 27 weight tiles
+  uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);                 // nslab input-plane slabs
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
+  uint64_t* sempty = sfull + kMaxSlabs;
+  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);                 // [4 warps][NT][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w_bytes);
+      for (int tap = 0; tap < 27; ++tap) tma_load_2d(wreg + (size_t)tap * p.w_tile_bytes, &tmB, wfull, 0, tap * p.Cout);
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int pi = 0; pi < sc.nd + 2; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          mbar_expect_tx(&sfull[slot], p.slab_tx);
+          tma_load_5d(slabs + (size_t)slot * p.slab_bytes, &tmA, &sfull[slot], 0, sc.w0 - 1, sc.h0 - 1, sc.d0 - 1 + pi, sc.b);
+          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================
+    // One thread, and its instruction stream is the critical path at small N (a 128xNx16 MMA occupies the tensor
+    // pipe for only ~64 cycles): everything but two 32-bit adds per MMA is hoisted out of the fully unrolled tap loop.
+    if (lane == 0) {
+      constexpr uint32_t ROWB = KC * 2u;
+      constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+      constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);   // SBO = 10 rows, version 1, swizzle
+      constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);        // SBO = 8 rows
+      constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t slab16 = p.slab_bytes >> 4;
+      const uint32_t nslab = (uint32_t)p.nslab;
+      mbar_wait(wfull, 0);
+      uint32_t slot0 = 0;                  // ring slot of the oldest plane (d-1) of the current output plane
+      uint32_t wslot = 0, wph = 0;         // next plane whose "full" barrier has not been waited on yet
+      uint32_t ahead = 0;                  // planes already waited on that belong to the current/future output planes
+      int local = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int i = 0; i < sc.nd; ++i, ++local) {
+          while (ahead < 3u) {
+            mbar_wait(&sfull[wslot], wph);
+            if (++wslot == nslab) { wslot = 0; wph ^= 1u; }
+            ++ahead;
+          }
+          const int acc = local & 1;
+          mbar_wait(&tempty[acc], (((uint32_t)local >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
+          uint32_t sl = slot0;
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const uint32_t a_kd = s_lo + sl * slab16;
+            if (++sl == nslab) sl = 0;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  const uint32_t a_lo = a_kd + (uint32_t)(((kh * HALO_W + kw) * ROWB + kk * 32u) >> 4);
+                  const uint32_t b_lo = w_lo + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TILE16 + kk * 2);
+                  asm volatile(
+                      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                      "setp.ne.b32 p, %6, 0;\n\t"
+                      "mov.b64 da, {%1, %2};\n\t"
+                      "mov.b64 db, {%3, %4};\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                      ::"r"(d_tmem), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(B_HI), "r"(idesc), "r"((kd | kh | kw | kk) ? 1u : 0u)
+                      : "memory");
+                }
+              }
+            }
+          }
+          tc_commit(&tfull[acc]);
+          tc_commit(&sempty[slot0]);                    // the oldest plane is no longer needed
+          if (++slot0 == nslab) slot0 = 0;
+          --ahead;
+        }
+        // the last two planes of the segment are not shared with the next segment
+        tc_commit(&sempty[slot0]);
+        if (++slot0 == nslab) slot0 = 0;
+        tc_commit(&sempty[slot0]);
+        if (++slot0 == nslab) slot0 = 0;
+        ahead -= 2u;
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) =========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % HW_T, lh = row / HW_T;
+    const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      const int oh = sc.h0 + lh, ow = sc.w0 + lw;
+      const bool valid = oh < p.H && ow < p.W;
+      float s1[NT], s2[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int i = 0; i < sc.nd; ++i, ++local) {
+        const int acc = local & 1;
+        __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs;
+        mbar_wait(&tfull[acc], ((uint32_t)local >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t raw[16];
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), raw);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+            if (!valid) v[j] = 0.f;
+            s1[c0 + j] += v[j];
+            s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
+          }
+          if (valid) {
+            if (p.scale) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
+            if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
+              uint4 lo, hi;
+              lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+              hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+              reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
+              reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (p.stats) {   // one partial per segment: reduce the per-row running sums over the 128 rows
+        float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
+          if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
+          const float s = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + (i >> 1)) * 2 + (i & 1)] = s;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -383,6 +628,66 @@ int pick_nt(int cout) {
   return 0;
 }
 
+// ---- halo-reuse (v2) planning ----
+struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab; uint32_t rowb, slab_bytes, w_tile_bytes, w_bytes; size_t smem; };
+
+HaloPlan plan_halo(const coma_conv_args& a) {
+  HaloPlan h{};
+  h.ok = false;
+  static const bool disabled = [] { const char* e = getenv("COMA_DISABLE_HALO"); return e && e[0] == '1'; }();
+  if (disabled || a.transposed || a.ksize != 3 || a.stride != 1) return h;
+  if (!(a.Cin == 16 || a.Cin == 32 || a.Cin == 64) || !(a.Cout == 16 || a.Cout == 32 || a.Cout == 64)) return h;
+  if (a.Wo < HW_T || a.Ho < HH_T) return h;              // tiny planes: the per-tap kernel wastes less
+  h.rowb = (uint32_t)a.Cin * 2u;
+  h.slab_bytes = ((uint32_t)HALO_ROWS * h.rowb + 1023u) & ~1023u;
+  h.w_tile_bytes = (uint32_t)a.Cout * h.rowb;
+  h.w_bytes = 27u * h.w_tile_bytes;
+  const size_t tail = (2 * kMaxSlabs + 1 + 4) * 8 + 16 + (size_t)4 * a.Cout * 2 * sizeof(float) + 64;
+  const size_t budget = 222 * 1024;
+  const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
+  if (fixed + 4 * (size_t)h.slab_bytes > budget) return h;
+  int nslab = (int)((budget - fixed) / h.slab_bytes);
+  h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
+  h.smem = fixed + (size_t)h.nslab * h.slab_bytes;
+  h.cols_w = (a.Wo + HW_T - 1) / HW_T;
+  h.cols_h = (a.Ho + HH_T - 1) / HH_T;
+  const int ncols = a.B * h.cols_w * h.cols_h;
+  int segs = (4 * num_sms() + ncols - 1) / ncols;
+  const int max_segs = (a.Do + 3) / 4;
+  if (segs > max_segs) segs = max_segs;
+  if (segs < 1) segs = 1;
+  h.DS = (a.Do + segs - 1) / segs;
+  h.segs_d = (a.Do + h.DS - 1) / h.DS;
+  h.ok = true;
+  return h;
+}
+
+template <int NT, int KC>
+int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
+  HaloParams p{};
+  p.B = a.B; p.D = a.Do; p.H = a.Ho; p.W = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = a.Cin;
+  p.cols_w = h.cols_w; p.cols_h = h.cols_h; p.segs_d = h.segs_d; p.DS = h.DS;
+  p.total_segs = a.B * h.cols_w * h.cols_h * h.segs_d;
+  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)HALO_ROWS * h.rowb;
+  p.w_tile_bytes = h.w_tile_bytes; p.w_bytes = h.w_bytes;
+  p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
+  p.stat_chunks = h.cols_w * h.cols_h * h.segs_d;
+  uint32_t cols = 32;
+  while (cols < 2u * NT) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = num_sms();
+  if (grid > p.total_segs) grid = p.total_segs;
+  conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  COMA_CHECK_LAUNCH("conv_halo");
+  return COMA_OK;
+}
+
 }  // namespace
 
 bool conv_tc_supported(const coma_conv_args& a) {
@@ -400,12 +705,45 @@ static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int&
 }
 
 int conv_tc_stat_chunks(const coma_conv_args& a) {
+  const HaloPlan h = plan_halo(a);
+  if (h.ok) return h.cols_w * h.cols_h * h.segs_d;
   int tw, th, td, cl;
   tile_counts(a, tw, th, td, cl);
   return tw * th * td * cl;
 }
 
+static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
+                             (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
+    cuuint32_t box[5] = {(cuuint32_t)a.Cin, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
+    if (!make_map(&tmA, base, 5, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)27 * a.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)a.Cin, (cuuint32_t)a.Cout};
+    cuuint32_t estr[2] = {1, 1};
+    if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
+  }
+#define COMA_HALO_CASE(NTV, KCV) if (a.Cout == NTV && a.Cin == KCV) return launch_halo<NTV, KCV>(a, h, tmA, tmB, stream);
+  COMA_HALO_CASE(16, 16) COMA_HALO_CASE(16, 32) COMA_HALO_CASE(16, 64)
+  COMA_HALO_CASE(32, 16) COMA_HALO_CASE(32, 32) COMA_HALO_CASE(32, 64)
+  COMA_HALO_CASE(64, 16) COMA_HALO_CASE(64, 32) COMA_HALO_CASE(64, 64)
+#undef COMA_HALO_CASE
+  set_error("conv_halo: unsupported channel combination");
+  return COMA_ERR_UNSUPPORTED;
+}
+
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
+  {
+    const HaloPlan h = plan_halo(a);
+    if (h.ok) return conv_halo_launch(a, h, stream);
+  }
   TcParams p{};
   p.B = a.B; p.Di = a.Di; p.Hi = a.Hi; p.Wi = a.Wi; p.Do = a.Do; p.Ho = a.Ho; p.Wo = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout;
   p.ksize = a.ksize; p.stride = a.stride; p.pad = a.pad; p.transposed = a.transposed;

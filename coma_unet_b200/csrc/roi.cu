@@ -31,10 +31,17 @@ __global__ void __launch_bounds__(256) roi_paint_kernel(coma_roi_paint_args a) {
         if (label == ids[i]) { loc = lut[2 * i]; sd = lut[2 * i + 1]; }
     }
     T* o = ob + v * a.out_cs;
-    Elem<T>::st(o, __ldg(prompt + v));
-    if (a.out_cs > 1) Elem<T>::st(o + 1, sd);
-    if (a.out_cs > 2) Elem<T>::st(o + 2, loc);
-    for (int c = 3; c < a.out_cs; ++c) Elem<T>::st(o + c, 0.f);
+    if ((a.out_cs & 7) == 0) {   // 16-byte vector stores: [prompt, saliency, suvr, 0, ...]
+      float vals[8] = {__ldg(prompt + v), sd, loc, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8(o, vals);
+      const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = 8; c < a.out_cs; c += 8) store8(o + c, zeros);
+    } else {
+      Elem<T>::st(o, __ldg(prompt + v));
+      if (a.out_cs > 1) Elem<T>::st(o + 1, sd);
+      if (a.out_cs > 2) Elem<T>::st(o + 2, loc);
+      for (int c = 3; c < a.out_cs; ++c) Elem<T>::st(o + c, 0.f);
+    }
   }
 }
 
@@ -62,9 +69,18 @@ __global__ void __launch_bounds__(256) pack2_kernel(coma_pack2_args a) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t v = i % a.V;
     T* o = d + i * a.dst_cs;
-    Elem<T>::st(o, Elem<T>::ld(pa + i) + (a.a_add ? __ldg(a.a_add + v) : 0.f));
-    Elem<T>::st(o + 1, Elem<T>::ld(pb + i));
-    for (int c = 2; c < a.dst_cs; ++c) Elem<T>::st(o + c, 0.f);
+    const float va = Elem<T>::ld(pa + i) + (a.a_add ? __ldg(a.a_add + v) : 0.f);
+    const float vb = pb ? Elem<T>::ld(pb + i) : 0.f;
+    if ((a.dst_cs & 7) == 0) {
+      float vals[8] = {va, vb, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8(o, vals);
+      const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = 8; c < a.dst_cs; c += 8) store8(o + c, zeros);
+    } else {
+      Elem<T>::st(o, va);
+      Elem<T>::st(o + 1, vb);
+      for (int c = 2; c < a.dst_cs; ++c) Elem<T>::st(o + c, 0.f);
+    }
   }
 }
 
@@ -77,7 +93,7 @@ __global__ void __launch_bounds__(256) unpack2_kernel(coma_unpack2_args a) {
     float s = 0.f;
     for (int b = 0; b < a.B; ++b) {
       const int64_t i = (int64_t)b * a.V + v;
-      const float g0 = Elem<T>::ld(d + i * a.dst_cs), g1 = Elem<T>::ld(d + i * a.dst_cs + 1);
+      const float g0 = Elem<T>::ld(d + i * a.dst_cs), g1 = db ? Elem<T>::ld(d + i * a.dst_cs + 1) : 0.f;
       if (da) Elem<T>::st(da + i, g0);
       if (db) Elem<T>::st(db + i, g1);
       s += g0;
@@ -183,7 +199,7 @@ extern "C" int coma_roi_paint_bwd(const void* dbuf, const float* is_pos, float* 
 }
 
 extern "C" int coma_pack2_fwd(const coma_pack2_args* a, coma_stream_t stream) {
-  COMA_CHECK_ARG(a && a->a && a->b && a->dst && a->dst_cs >= 2, "coma_pack2_fwd: bad arguments");
+  COMA_CHECK_ARG(a && a->a && a->dst && a->dst_cs >= 2, "coma_pack2_fwd: bad arguments");   // b may be NULL (zeros)
   if (a->dtype == COMA_BF16) pack2_kernel<__nv_bfloat16><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
   else pack2_kernel<float><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
   COMA_CHECK_LAUNCH("pack2");

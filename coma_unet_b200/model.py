@@ -167,6 +167,9 @@ class ObservableAttentionUnet(nn.Module):
     def _backbone(self, xv, covariate):
         """NDHWC in, NDHWC out: (x[B,D,H,W,out], encoder tensors, decoder tensors)."""
         head, encdec, reduce_channels = self.model
+        if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1:
+            # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the tensor-core path
+            xv = ops.Pack2Fn.apply(xv, None, None, 16)
         h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
         d, encs, decs = encdec(h, covariate)
         return reduce_channels(d, covariate=covariate), encs, decs

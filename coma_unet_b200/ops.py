@@ -540,7 +540,7 @@ class Pack2Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a_t, a_add, b_t, cs):
-        a_t, b_t = a_t.contiguous(), b_t.contiguous()
+        a_t, b_t = a_t.contiguous(), (None if b_t is None else b_t.contiguous())
         B, D, H, W, _ = a_t.shape
         V = D * H * W
         dst = torch.empty(B, D, H, W, cs, device=a_t.device, dtype=a_t.dtype)
@@ -560,6 +560,8 @@ class Pack2Fn(torch.autograd.Function):
         V = D * H * W
         da = torch.empty(ctx.shape, device=ddst.device, dtype=ddst.dtype) if ctx.needs_input_grad[0] else None
         db = torch.empty(ctx.shape, device=ddst.device, dtype=ddst.dtype) if ctx.needs_input_grad[2] else None
+        if da is None and db is None and ctx.add_shape is None:
+            return None, None, None, None
         dadd = torch.empty(V, device=ddst.device, dtype=torch.float32) if ctx.add_shape is not None else None
         a = L.Unpack2Args()
         a.ddst, a.da, a.db, a.d_a_add = L.ptr(ddst), L.ptr(da), L.ptr(db), L.ptr(dadd)

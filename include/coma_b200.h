@@ -211,7 +211,7 @@ typedef struct {
 } coma_roi_paint_args;
 int coma_roi_paint(const coma_roi_paint_args* a, coma_stream_t stream);
 
-/* dst[b,v,0] = a[b,v] + (a_add ? a_add[v] : 0); dst[b,v,1] = b[b,v]; dst[b,v,2..] = 0   (replaces the
+/* dst[b,v,0] = a[b,v] + (a_add ? a_add[v] : 0); dst[b,v,1] = b ? b[b,v] : 0; dst[b,v,2..] = 0   (replaces the
  * `general_prompt + ...` add and the two torch.cat calls at attn_unet_data_parallel.py:651,654) */
 typedef struct {
   const void* a; const float* a_add; const void* b; void* dst;

@@ -338,6 +338,11 @@ TC_CASES = [
     (2, 64, 32, 8, 8, 8, 3, 2, True),        # transposed: 8 parity classes
     (1, 32, 16, 5, 3, 6, 3, 2, True),
     (2, 64, 32, 8, 8, 8, 1, 1, False),
+    # halo-reuse kernel (k3 s1, Cin/Cout <= 64, planes >= 16 x 8)
+    (1, 64, 32, 6, 20, 13, 3, 1, False),     # ragged in every dim, two d-segments
+    (1, 16, 16, 9, 16, 8, 3, 1, False),      # exactly one tile per plane, 32B swizzle
+    (2, 32, 64, 5, 32, 24, 3, 1, False),
+    (1, 32, 16, 20, 17, 9, 3, 1, False),
 ]
 
 
