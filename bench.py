@@ -233,6 +233,10 @@ def kernel_profile(step_fn, n=2):
             flops = conv_flops_of_call(name, a)
             tc = bool(_lib.lib().coma_conv3d_tcgen05_supported(cargs[0])) and a.impl != _lib.IMPL_SIMT
             shape = (a.B, a.Cin, a.Cout, a.Do, a.ksize, a.stride, a.transposed)
+        elif name in ("coma_conv3d_wgrad", "coma_convT3d_wgrad"):
+            a = cargs[0]._obj
+            flops = 2.0 * a.B * a.Dg * a.Hg * a.Wg * a.ksize ** 3 * a.Cg * a.Cx
+            shape = (a.B, a.Cg, a.Cx, a.Dg, a.ksize, a.stride, 0)
         else:
             shape = ()
         records.append((name, tc, flops, e0, e1, shape))

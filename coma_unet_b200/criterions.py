@@ -112,12 +112,10 @@ class GenerativeContrastiveLoss(nn.Module):
     def forward(self, prediction, target, roi, final_representations, intermediate_extractions):
         gen = self.gen_loss(prediction, target, roi)
         reduced = gen.sum() if self.gen_loss.batch_reduction is None else gen
-        if self.reg_weight == 0:
-            # weight 0 in the shipped config (validation.py:154): skip the dead TripletMarginLoss kernels
-            ps = torch.zeros((), device=gen.device)
-        else:
-            ps = self.reg_weight * self.get_pred_space_contra_loss(final_representations)
-            if ps.device != gen.device:
-                ps = ps.to(gen.device)
+        # evaluated even with weight 0 (validation.py:154): its zero gradient is what makes AdamW decay
+        # final_projection_head in the reference (grad == 0, not None)
+        ps = self.reg_weight * self.get_pred_space_contra_loss(final_representations)
+        if ps.device != gen.device:
+            ps = ps.to(gen.device)
         ds = self.ds_reg_weight * self.get_ds_contra_loss(intermediate_extractions)
         return self.gen_weight * reduced + ps + ds, gen, ps, ds

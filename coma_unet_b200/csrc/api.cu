@@ -19,6 +19,8 @@ void set_error(const char* fmt, ...) {
 int conv_simt_stat_chunks(const coma_conv_args& a);
 int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream);
 int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream);
+bool wgrad_mma_supported(const coma_wgrad_args& a);
+int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool conv_tc_supported(const coma_conv_args& a);
 int conv_tc_stat_chunks(const coma_conv_args& a);
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream);
@@ -107,11 +109,15 @@ static int check_wgrad(const coma_wgrad_args* a, const char* who) {
                      a->Wg == (a->Wx + 2 * a->pad - a->ksize) / a->stride + 1, "%s: extents do not match the conv geometry", who);
   return COMA_OK;
 }
+static int run_wgrad(const coma_wgrad_args* a, cudaStream_t stream) {
+  if (a->impl != COMA_IMPL_SIMT && wgrad_mma_supported(*a)) return wgrad_mma_launch(*a, stream);
+  return wgrad_simt_launch(*a, stream);
+}
 extern "C" int coma_conv3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream) {
   if (int rc = check_wgrad(a, "coma_conv3d_wgrad")) return rc;
-  return wgrad_simt_launch(*a, stream);
+  return run_wgrad(a, stream);
 }
 extern "C" int coma_convT3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream) {
   if (int rc = check_wgrad(a, "coma_convT3d_wgrad")) return rc;
-  return wgrad_simt_launch(*a, stream);
+  return run_wgrad(a, stream);
 }

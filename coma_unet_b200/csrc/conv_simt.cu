@@ -224,8 +224,78 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(coma_wgrad_args a, int6
   }
 }
 
+// Cg == 1 (gradients of the 1-channel heads: psi, 16->1 / 8->1 modulator convs, projection heads): a per-voxel
+// scaled accumulation of x, one tap per blockIdx.y; HBM-bound (reads g and the shifted x once per tap).
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_cg1_kernel(coma_wgrad_args a, int64_t vchunk) {
+  constexpr int CXMAX = 64;
+  __shared__ float red[8][CXMAX];
+  const int K = a.ksize;
+  const int tap = blockIdx.y;
+  const int kd = tap / (K * K), kh = (tap / K) % K, kw = tap % K;
+  const int64_t Vg = (int64_t)a.Dg * a.Hg * a.Wg, total = (int64_t)a.B * Vg;
+  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, total);
+  const T* gp = static_cast<const T*>(a.g) + a.g_co;
+  const T* xp = static_cast<const T*>(a.x) + a.x_co;
+  const bool vec = (a.Cx % 8 == 0) && (a.x_cs % 8 == 0) && (a.x_co % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+  float acc[CXMAX];
+#pragma unroll
+  for (int c = 0; c < CXMAX; ++c) acc[c] = 0.f;
+  for (int64_t o = begin + threadIdx.x; o < end; o += 256) {
+    const float gv = Elem<T>::ld(gp + o * a.g_cs);
+    const int64_t bb = o / Vg, rem = o - bb * Vg;
+    const int ow = (int)(rem % a.Wg), t2 = (int)(rem / a.Wg);
+    const int oh = t2 % a.Hg, od = t2 / a.Hg;
+    const int id = od * a.stride + kd - a.pad, ih = oh * a.stride + kh - a.pad, iw = ow * a.stride + kw - a.pad;
+    if (id < 0 || id >= a.Dx || ih < 0 || ih >= a.Hx || iw < 0 || iw >= a.Wx) continue;
+    const T* xr = xp + (((bb * a.Dx + id) * a.Hx + ih) * a.Wx + iw) * a.x_cs;
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < CXMAX; c += 8) {
+        if (c < a.Cx) {
+          float xv[8];
+          load8(xr + c, xv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[c + e] = fmaf(gv, xv[e], acc[c + e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CXMAX; ++c)
+        if (c < a.Cx) acc[c] = fmaf(gv, Elem<T>::ld(xr + c), acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CXMAX; ++c) {
+    if (c < a.Cx) {
+      const float s = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.Cx) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(a.dw + (int64_t)tap * a.Cx + threadIdx.x, s);
+  }
+}
+
 int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
+  if (a.Cg == 1 && a.Cx <= 64) {
+    const int taps = a.ksize * a.ksize * a.ksize;
+    int64_t want = (int64_t)num_sms() * 8 / taps;
+    if (want < 1) want = 1;
+    int64_t vchunk = (total + want - 1) / want;
+    if (vchunk < 2048) vchunk = 2048;
+    const int64_t nch = (total + vchunk - 1) / vchunk;
+    dim3 grid((unsigned)nch, (unsigned)taps);
+    if (a.dtype == COMA_BF16) wgrad_cg1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, vchunk);
+    else wgrad_cg1_kernel<float><<<grid, 256, 0, stream>>>(a, vchunk);
+    COMA_CHECK_LAUNCH("wgrad_cg1");
+    return COMA_OK;
+  }
   int64_t nchunks = (total + 255) / 256;
   if (nchunks > 512) nchunks = 512;
   int64_t vchunk = (total + nchunks - 1) / nchunks;

@@ -71,14 +71,14 @@ def _round_up(n: int, m: int) -> int:
 # ------------------------------------------------------------------------------------------------
 # weight packing (cached)
 # ------------------------------------------------------------------------------------------------
-_pack_cache: dict = {}
-
-
 def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp: int, dtype: torch.dtype) -> torch.Tensor:
-    """Conv3d ``[Cout,Cin,k,k,k]`` / ConvTranspose3d ``[Cin,Cout,k,k,k]`` -> ``[k^3, cout_comp, cin_buf]`` (zero padded)."""
-    key = (id(weight), transposed, cin_buf, cout_comp, dtype)
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1].device == weight.device:
+    """Conv3d ``[Cout,Cin,k,k,k]`` / ConvTranspose3d ``[Cin,Cout,k,k,k]`` -> ``[k^3, cout_comp, cin_buf]`` (zero padded).
+
+    Cached on the parameter object itself (so the cache dies with it) and keyed by its version counter and storage."""
+    cache = weight.__dict__.setdefault("_coma_packed", {})
+    key = (transposed, cin_buf, cout_comp, dtype)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == (weight._version, weight.data_ptr(), weight.device):
         return hit[1]
     w = weight.detach()
     k = w.shape[2]
@@ -92,7 +92,7 @@ def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp:
         q[:, :p.shape[1], :p.shape[2]] = p
         p = q
     p = p.to(dtype).contiguous()
-    _pack_cache[key] = (weight._version, p)
+    cache[key] = ((weight._version, weight.data_ptr(), weight.device), p)
     return p
 
 

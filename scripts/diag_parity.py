@@ -80,3 +80,33 @@ for dt in (torch.float32, torch.bfloat16):
         print(f"      enc{i} scaled {check.scaled_err(a.cpu().numpy(), b.cpu().numpy()):.2e}")
     for i, (a, b) in enumerate(zip(pd, rd)):
         print(f"      dec{i} scaled {check.scaled_err(a.cpu().numpy(), b.cpu().numpy()):.2e}")
+
+# ---- calibration of bf16 GRADIENTS: torch autocast on the oracle vs fp32 oracle (train step) ----
+o32 = common.fill_deterministic(omodel.ContrastiveAttentionUNET_DP(3, 1, 1, case["channels"], [2] * 5, **kw), case["seed"]).to(DEV)
+oac = common.fill_deterministic(omodel.ContrastiveAttentionUNET_DP(3, 1, 1, case["channels"], [2] * 5, **kw), case["seed"]).to(DEV)
+g32 = run(o32, ocrit, case)[3]
+
+
+def run_autocast(model):
+    mri, tau, roi, covars, dicts = common.synthetic_batch(case["batch"], case["shape"], case["seed"])
+    mri, tau, roi = mri.to(DEV), tau.to(DEV), roi.to(DEV)
+    model.train(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred, proj, final = model(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    z = torch.zeros(final.size(), device=DEV)
+    loss, gen, _, _ = crit(ocrit)(pred.float(), tau, roi, (final.float(), z, z), (proj[-1].float(), covars[:, -1].float().to(DEV)))
+    loss.backward()
+    return {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+
+
+gac = run_autocast(oac)
+mb = common.fill_deterministic(cu.ContrastiveAttentionUNET_DP(3, 1, 1, case["channels"], [2] * 5, compute_dtype=torch.bfloat16, **kw), case["seed"]).to(DEV)
+gb = run(mb, cu, case)[3]
+print("train-step gradient cosine vs fp32 oracle:   torch-autocast-bf16   this-repo-bf16")
+for k in ["model.0.conv.0.conv.weight", "model.0.conv.0.film.2.weight", "model.1.submodule.0.conv.0.conv.weight",
+          "model.1.submodule.0.conv.1.conv.weight", "model.1.merge.conv.weight", "model.1.upconv.up.conv.weight",
+          "model.1.attention.W_g.0.conv.weight", "final_pred_head.conv.weight", "general_dynamic_prompt"]:
+    def cosine(a, b):
+        a, b = a.float().flatten().double(), b.float().flatten().double()
+        return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+    print(f"  {k:60s} {cosine(gac[k], g32[k]):.4f}   {cosine(gb[k], g32[k]):.4f}")

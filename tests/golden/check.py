@@ -17,10 +17,10 @@ def load():
     return data, meta
 
 
-def rel_err(a: np.ndarray, b: np.ndarray) -> float:
-    """max |a-b| / max(|b|, 1e-3*max|b|)  (SURVEY.md section 7 hard part 7)."""
+def rel_err(a: np.ndarray, b: np.ndarray, floor_frac: float = 1e-3) -> float:
+    """Per-voxel relative error max |a-b| / max(|b|, floor_frac*max|b|)  (SURVEY.md section 7 hard part 7)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    floor = 1e-3 * max(np.abs(b).max(), 1e-30)
+    floor = floor_frac * max(np.abs(b).max(), 1e-30)
     return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max())
 
 
