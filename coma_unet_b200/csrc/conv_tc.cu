@@ -577,6 +577,223 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ================================================================================================
+// v2-T: halo-reuse kernel for the transposed convolution (k3, s2, p1, op1), Cin, Cout <= 64.
+// M tile = 8(w) x 16(h) voxels of one INPUT plane; the 9 x 17 slab of that plane (+1 halo on the high side) and of
+// the next plane serve all 27 taps; the 8 output-parity classes accumulate in 8 TMEM accumulators
+// (class (pd,ph,pw): per dim parity 0 -> tap k=1 shift 0, parity 1 -> taps k=0 shift +1 and k=2 shift 0) and the
+// epilogue scatters each to its strided output voxels (2d+pd, 2h+ph, 2w+pw).
+// ================================================================================================
+constexpr int HT_W = HW_T + 1, HT_H = HH_T + 1, HT_ROWS = HT_W * HT_H;
+
+template <int NT, int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  constexpr int NACC = (8 * NT * 2 <= 512) ? 2 : 1;     // accumulator sets (8 classes each)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;
+  uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
+  uint64_t* sempty = sfull + kMaxSlabs;
+  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w_bytes);
+      for (int tap = 0; tap < 27; ++tap) tma_load_2d(wreg + (size_t)tap * p.w_tile_bytes, &tmB, wfull, 0, tap * p.Cout);
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int pi = 0; pi < sc.nd + 1; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          mbar_expect_tx(&sfull[slot], p.slab_tx);
+          tma_load_5d(slabs + (size_t)slot * p.slab_bytes, &tmA, &sfull[slot], 0, sc.w0, sc.h0, sc.d0 + pi, sc.b);
+          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t ROWB = KC * 2u;
+      constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+      constexpr uint32_t A_HI = ((HT_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+      constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+      constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t slab16 = p.slab_bytes >> 4;
+      const uint32_t nslab = (uint32_t)p.nslab;
+      mbar_wait(wfull, 0);
+      uint32_t slot0 = 0, wslot = 0, wph = 0, ahead = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int i = 0; i < sc.nd; ++i, ++local) {
+          while (ahead < 2u) {
+            mbar_wait(&sfull[wslot], wph);
+            if (++wslot == nslab) { wslot = 0; wph ^= 1u; }
+            ++ahead;
+          }
+          const int acc = NACC == 2 ? (local & 1) : 0;
+          const uint32_t par = NACC == 2 ? (((uint32_t)local >> 1) & 1u) : ((uint32_t)local & 1u);
+          mbar_wait(&tempty[acc], par ^ 1u);
+          tc_fence_after();
+          const uint32_t d_base = tmem_base + (uint32_t)(acc * 8 * NT);
+          const uint32_t a_pl0 = s_lo + slot0 * slab16;
+          const uint32_t a_pl1 = s_lo + ((slot0 + 1u == nslab) ? 0u : slot0 + 1u) * slab16;
+#pragma unroll
+          for (int cls = 0; cls < 8; ++cls) {
+            const int pw = cls & 1, ph = (cls >> 1) & 1, pd = (cls >> 2) & 1;
+            bool first = true;
+#pragma unroll
+            for (int id = 0; id <= pd; ++id) {
+#pragma unroll
+              for (int ih = 0; ih <= ph; ++ih) {
+#pragma unroll
+                for (int iw = 0; iw <= pw; ++iw) {
+                  const int kd = pd ? (id ? 2 : 0) : 1, kh = ph ? (ih ? 2 : 0) : 1, kw = pw ? (iw ? 2 : 0) : 1;
+                  const int sd = (pd && !id) ? 1 : 0, sh = (ph && !ih) ? 1 : 0, sw = (pw && !iw) ? 1 : 0;
+                  const uint32_t a_pl = sd ? a_pl1 : a_pl0;
+#pragma unroll
+                  for (int kk = 0; kk < KC / 16; ++kk) {
+                    const uint32_t a_lo = a_pl + (uint32_t)(((sh * HT_W + sw) * ROWB + kk * 32u) >> 4);
+                    const uint32_t b_lo = w_lo + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TILE16 + kk * 2);
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                        "setp.ne.b32 p, %6, 0;\n\t"
+                        "mov.b64 da, {%1, %2};\n\t"
+                        "mov.b64 db, {%3, %4};\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                        ::"r"(d_base + (uint32_t)(cls * NT)), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(B_HI), "r"(idesc),
+                          "r"((first && kk == 0) ? 0u : 1u)
+                        : "memory");
+                  }
+                  first = false;
+                }
+              }
+            }
+          }
+          tc_commit(&tfull[acc]);
+          tc_commit(&sempty[slot0]);
+          if (++slot0 == nslab) slot0 = 0;
+          --ahead;
+        }
+        tc_commit(&sempty[slot0]);       // the segment's last plane (only its "+1" role was used)
+        if (++slot0 == nslab) slot0 = 0;
+        --ahead;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % HW_T, lh = row / HW_T;
+    const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      const int ih = sc.h0 + lh, iw = sc.w0 + lw;
+      const bool valid = ih < p.H && iw < p.W;
+      float s1[NT], s2[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int i = 0; i < sc.nd; ++i, ++local) {
+        const int acc = NACC == 2 ? (local & 1) : 0;
+        const uint32_t par = NACC == 2 ? (((uint32_t)local >> 1) & 1u) : ((uint32_t)local & 1u);
+        mbar_wait(&tfull[acc], par);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cls = 0; cls < 8; ++cls) {
+          const int od = 2 * (sc.d0 + i) + ((cls >> 2) & 1), oh = 2 * ih + ((cls >> 1) & 1), ow = 2 * iw + (cls & 1);
+          __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * Do + od) * Ho + oh) * Wo + ow) * p.y_cs;
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t raw[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 8 * NT + cls * NT + c0), raw);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+              if (!valid) v[j] = 0.f;
+              s1[c0 + j] += v[j];
+              s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
+            }
+            if (valid) {
+              if (p.scale) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
+              if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+                hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+                reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
+                reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (p.stats) {
+        float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
+          if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
+          const float s = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + (i >> 1)) * 2 + (i & 1)] = s;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -635,11 +852,13 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   HaloPlan h{};
   h.ok = false;
   static const bool disabled = [] { const char* e = getenv("COMA_DISABLE_HALO"); return e && e[0] == '1'; }();
-  if (disabled || a.transposed || a.ksize != 3 || a.stride != 1) return h;
+  if (disabled || a.ksize != 3) return h;
+  if (a.transposed ? a.stride != 2 : a.stride != 1) return h;
   if (!(a.Cin == 16 || a.Cin == 32 || a.Cin == 64) || !(a.Cout == 16 || a.Cout == 32 || a.Cout == 64)) return h;
-  if (a.Wo < HW_T || a.Ho < HH_T) return h;              // tiny planes: the per-tap kernel wastes less
+  const int gw = a.transposed ? a.Wi : a.Wo, gh = a.transposed ? a.Hi : a.Ho, gd = a.transposed ? a.Di : a.Do;
+  if (gw < HW_T || gh < HH_T) return h;                  // tiny planes: the per-tap kernel wastes less
   h.rowb = (uint32_t)a.Cin * 2u;
-  h.slab_bytes = ((uint32_t)HALO_ROWS * h.rowb + 1023u) & ~1023u;
+  h.slab_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
   h.w_tile_bytes = (uint32_t)a.Cout * h.rowb;
   h.w_bytes = 27u * h.w_tile_bytes;
   const size_t tail = (2 * kMaxSlabs + 1 + 4) * 8 + 16 + (size_t)4 * a.Cout * 2 * sizeof(float) + 64;
@@ -649,15 +868,15 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   int nslab = (int)((budget - fixed) / h.slab_bytes);
   h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
   h.smem = fixed + (size_t)h.nslab * h.slab_bytes;
-  h.cols_w = (a.Wo + HW_T - 1) / HW_T;
-  h.cols_h = (a.Ho + HH_T - 1) / HH_T;
+  h.cols_w = (gw + HW_T - 1) / HW_T;
+  h.cols_h = (gh + HH_T - 1) / HH_T;
   const int ncols = a.B * h.cols_w * h.cols_h;
   int segs = (4 * num_sms() + ncols - 1) / ncols;
-  const int max_segs = (a.Do + 3) / 4;
+  const int max_segs = (gd + 3) / 4;
   if (segs > max_segs) segs = max_segs;
   if (segs < 1) segs = 1;
-  h.DS = (a.Do + segs - 1) / segs;
-  h.segs_d = (a.Do + h.DS - 1) / h.DS;
+  h.DS = (gd + segs - 1) / segs;
+  h.segs_d = (gd + h.DS - 1) / h.DS;
   h.ok = true;
   return h;
 }
@@ -665,25 +884,29 @@ HaloPlan plan_halo(const coma_conv_args& a) {
 template <int NT, int KC>
 int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
   HaloParams p{};
-  p.B = a.B; p.D = a.Do; p.H = a.Ho; p.W = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = a.Cin;
+  const bool tr = a.transposed != 0;
+  p.B = a.B; p.D = tr ? a.Di : a.Do; p.H = tr ? a.Hi : a.Ho; p.W = tr ? a.Wi : a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = a.Cin;
   p.cols_w = h.cols_w; p.cols_h = h.cols_h; p.segs_d = h.segs_d; p.DS = h.DS;
   p.total_segs = a.B * h.cols_w * h.cols_h * h.segs_d;
-  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)HALO_ROWS * h.rowb;
+  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb;
   p.w_tile_bytes = h.w_tile_bytes; p.w_bytes = h.w_bytes;
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
   p.stat_chunks = h.cols_w * h.cols_h * h.segs_d;
   uint32_t cols = 32;
-  while (cols < 2u * NT) cols <<= 1;
+  const uint32_t need = tr ? ((8u * NT * 2u <= 512u) ? 16u * NT : 8u * NT) : 2u * NT;
+  while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   int grid = num_sms();
   if (grid > p.total_segs) grid = p.total_segs;
-  conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  if (tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
   return COMA_OK;
 }
@@ -718,7 +941,7 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
     cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
                              (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
-    cuuint32_t box[5] = {(cuuint32_t)a.Cin, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)a.Cin, (cuuint32_t)(a.transposed ? HT_W : HALO_W), (cuuint32_t)(a.transposed ? HT_H : HALO_H), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
     if (!make_map(&tmA, base, 5, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;

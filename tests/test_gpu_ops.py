@@ -343,6 +343,11 @@ TC_CASES = [
     (1, 16, 16, 9, 16, 8, 3, 1, False),      # exactly one tile per plane, 32B swizzle
     (2, 32, 64, 5, 32, 24, 3, 1, False),
     (1, 32, 16, 20, 17, 9, 3, 1, False),
+    # halo-reuse transposed kernel (8 parity classes in 8 TMEM accumulators)
+    (2, 64, 32, 6, 16, 8, 3, 2, True),
+    (1, 32, 16, 5, 20, 13, 3, 2, True),      # ragged
+    (1, 64, 64, 4, 16, 16, 3, 2, True),      # single accumulator set (8 x 64 columns)
+    (1, 16, 16, 9, 17, 9, 3, 2, True),
 ]
 
 
