@@ -109,6 +109,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp (all 32 lanes must call it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of `swz` bytes, 8-row groups
 // `8*swz` bytes apart (SBO), version 1 (sm_100), layout = 2 (128B) / 4 (64B) / 6 (32B swizzle).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
@@ -212,14 +223,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    if (lane == 0) {
+    {
+      // warp-uniform loop (descriptors in uniform registers), one elected lane issues
+      const bool leader = elect_one();
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t layout = p.swz == 128 ? 2u : (p.swz == 64 ? 4u : 6u);
+      const uint32_t hi = ((8u * (uint32_t)p.swz) >> 4) | (1u << 14) | (layout << 29);
+      const uint32_t base_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t stage16 = p.stage_bytes >> 4, a16 = p.a_bytes >> 4;
+      const int kk_n = p.KC >> 4;
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
-        const TileCoord tc = decode_tile(p, t);
-        const int ksteps = num_taps(p, tc.cls) * p.kchunks;
+        // k-steps of this tile: taps x channel chunks (the parity class is the slowest-but-one tile index)
+        int ksteps;
+        if (!p.transposed) {
+          ksteps = p.ksize * p.ksize * p.ksize * p.kchunks;
+        } else {
+          const int cls = (t / (p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_d)) % p.classes;
+          ksteps = num_taps(p, cls) * p.kchunks;
+        }
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -228,18 +252,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_bytes;
-          const uint64_t adesc = make_desc(a_addr, p.swz), bdesc = make_desc(b_addr, p.swz);
-          const int kk_n = p.KC >> 4;
-          for (int kk = 0; kk < kk_n; ++kk) {
-            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ks | kk) ? 1u : 0u);
+          const uint32_t a_lo = base_lo + (uint32_t)stage * stage16;
+          const uint32_t b_lo = a_lo + a16;
+          if (leader) {
+            for (int kk = 0; kk < kk_n; ++kk) {
+              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                  "setp.ne.b32 p, %5, 0;\n\t"
+                  "mov.b64 da, {%1, %3};\n\t"
+                  "mov.b64 db, {%2, %3};\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                  ::"r"(d_tmem), "r"(a_lo + (uint32_t)(kk * 2)), "r"(b_lo + (uint32_t)(kk * 2)), "r"(hi), "r"(idesc),
+                    "r"((ks | kk) ? 1u : 0u)
+                  : "memory");
+            }
+            tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
           }
-          tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);              // accumulator complete -> epilogue
+        if (leader) tc_commit(&tfull[acc]);    // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -430,7 +464,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================ MMA issuer ===================================
     // One thread, and its instruction stream is the critical path at small N (a 128xNx16 MMA occupies the tensor
     // pipe for only ~64 cycles): everything but two 32-bit adds per MMA is hoisted out of the fully unrolled tap loop.
-    if (lane == 0) {
+    {
+      // the whole warp runs the (warp-uniform) loop so descriptors live in uniform registers; one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t ROWB = KC * 2u;
       constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
       constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);   // SBO = 10 rows, version 1, swizzle
@@ -471,7 +507,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kk = 0; kk < KC / 16; ++kk) {
                   const uint32_t a_lo = a_kd + (uint32_t)(((kh * HALO_W + kw) * ROWB + kk * 32u) >> 4);
                   const uint32_t b_lo = w_lo + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TILE16 + kk * 2);
-                  asm volatile(
+                  if (leader) asm volatile(
                       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
                       "setp.ne.b32 p, %6, 0;\n\t"
                       "mov.b64 da, {%1, %2};\n\t"
@@ -483,16 +519,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          tc_commit(&tfull[acc]);
-          tc_commit(&sempty[slot0]);                    // the oldest plane is no longer needed
+          if (leader) {
+            tc_commit(&tfull[acc]);
+            tc_commit(&sempty[slot0]);                  // the oldest plane is no longer needed
+          }
+          __syncwarp();
           if (++slot0 == nslab) slot0 = 0;
           --ahead;
         }
         // the last two planes of the segment are not shared with the next segment
-        tc_commit(&sempty[slot0]);
+        if (leader) tc_commit(&sempty[slot0]);
         if (++slot0 == nslab) slot0 = 0;
-        tc_commit(&sempty[slot0]);
+        if (leader) tc_commit(&sempty[slot0]);
         if (++slot0 == nslab) slot0 = 0;
+        __syncwarp();
         ahead -= 2u;
       }
     }
@@ -637,7 +677,8 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t ROWB = KC * 2u;
       constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
       constexpr uint32_t A_HI = ((HT_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
@@ -683,7 +724,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int kk = 0; kk < KC / 16; ++kk) {
                     const uint32_t a_lo = a_pl + (uint32_t)(((sh * HT_W + sw) * ROWB + kk * 32u) >> 4);
                     const uint32_t b_lo = w_lo + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TILE16 + kk * 2);
-                    asm volatile(
+                    if (leader) asm volatile(
                         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
                         "setp.ne.b32 p, %6, 0;\n\t"
                         "mov.b64 da, {%1, %2};\n\t"
@@ -698,12 +739,16 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          tc_commit(&tfull[acc]);
-          tc_commit(&sempty[slot0]);
+          if (leader) {
+            tc_commit(&tfull[acc]);
+            tc_commit(&sempty[slot0]);
+          }
+          __syncwarp();
           if (++slot0 == nslab) slot0 = 0;
           --ahead;
         }
-        tc_commit(&sempty[slot0]);       // the segment's last plane (only its "+1" role was used)
+        if (leader) tc_commit(&sempty[slot0]);       // the segment's last plane (only its "+1" role was used)
+        __syncwarp();
         if (++slot0 == nslab) slot0 = 0;
         --ahead;
       }
