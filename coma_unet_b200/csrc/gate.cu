@@ -61,6 +61,154 @@ __global__ void __launch_bounds__(128) gate_fused_kernel(coma_gate_args a) {
   }
 }
 
+
+// ---- bf16 tensor-core variant (mma.sync m16n8k16): the two 1x1x1 convolutions of the gate are a [32 voxels x 2C] x [2C x C/2]
+// GEMM per warp iteration, so the kernel becomes HBM-bound (3*C*2 bytes per voxel) instead of FMA/LDS-bound. ----
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) gate_mma_kernel(coma_gate_args a) {
+  constexpr int F = C / 2, LD = C + 8, NTILES = F / 8, CV = C / 8;
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __nv_bfloat16* swg = reinterpret_cast<__nv_bfloat16*>(gsm);            // [F][LD]
+  __nv_bfloat16* swx = swg + F * LD;                                      // [F][LD]
+  __nv_bfloat16* tiles = swx + F * LD;                                    // [8 warps][2][32][LD]
+  float* sb = reinterpret_cast<float*>(tiles + 8 * 2 * 32 * LD);          // [F]
+  float* sp = sb + F;                                                     // [F]
+  float* satt = sp + F;                                                   // [8][32]
+  for (int i = threadIdx.x; i < F * C; i += 256) {
+    swg[(i / C) * LD + (i % C)] = __float2bfloat16_rn(a.wg[i]);
+    swx[(i / C) * LD + (i % C)] = __float2bfloat16_rn(a.wx[i]);
+  }
+  for (int i = threadIdx.x; i < F; i += 256) { sb[i] = a.bsum[i]; sp[i] = a.wpsi[i]; }
+  __syncthreads();
+  const float bpsi = a.bpsi_ptr ? __ldg(a.bpsi_ptr) : a.bpsi;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __nv_bfloat16* tg = tiles + (size_t)warp * 2 * 32 * LD;
+  __nv_bfloat16* tx = tg + 32 * LD;
+  float* att = satt + warp * 32;
+  const int64_t total = (int64_t)a.B * a.V, ntiles = (total + 31) / 32;
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(a.g) + a.g_co;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(a.x) + a.x_co;
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(a.out) + a.out_co;
+  for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < ntiles; tile += (int64_t)gridDim.x * 8) {
+    const int64_t v0 = tile * 32;
+#pragma unroll
+    for (int i = 0; i < CV; ++i) {
+      const int idx = lane + 32 * i, row = idx / CV, vec = (idx % CV) * 8;
+      const int64_t v = v0 + row;
+      uint4 gv = make_uint4(0, 0, 0, 0), xv = make_uint4(0, 0, 0, 0);
+      if (v < total) {
+        gv = __ldg(reinterpret_cast<const uint4*>(gp + v * a.g_cs + vec));
+        xv = __ldg(reinterpret_cast<const uint4*>(xp + v * a.x_cs + vec));
+      }
+      *reinterpret_cast<uint4*>(tg + row * LD + vec) = gv;
+      *reinterpret_cast<uint4*>(tx + row * LD + vec) = xv;
+    }
+    __syncwarp();
+    float acc[2][NTILES][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < NTILES; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
+    const int mat = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const __nv_bfloat16* ta = half ? tx : tg;
+      const __nv_bfloat16* tw = half ? swx : swg;
+#pragma unroll
+      for (int k0 = 0; k0 < C; k0 += 16) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) ldsm_x4(af[m], ta + (m * 16 + (mat & 1) * 8 + r) * LD + k0 + (mat >> 1) * 8);
+        if constexpr (NTILES >= 2) {
+#pragma unroll
+          for (int n = 0; n < NTILES; n += 2) {
+            uint32_t bf[4];
+            ldsm_x4(bf, tw + (n * 8 + (mat >> 1) * 8 + r) * LD + k0 + (mat & 1) * 8);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              mma16816(acc[m][n], af[m], bf[0], bf[1]);
+              mma16816(acc[m][n + 1], af[m], bf[2], bf[3]);
+            }
+          }
+        } else {
+          uint32_t bf[2];
+          ldsm_x2(bf, tw + ((lane & 7)) * LD + k0 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) mma16816(acc[m][0], af[m], bf[0], bf[1]);
+        }
+      }
+    }
+    // q = sum_f wpsi[f] * relu(t[f] + b[f]);  accumulator: (e&1) -> column 2*(lane%4)+(e&1), (e>>1) -> row lane/4 + 8*(e>>1)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < NTILES; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = n * 8 + (lane & 3) * 2 + (e & 1);
+          const float t = fmaxf(acc[m][n][e] + sb[col], 0.f) * sp[col];
+          if (e < 2) q0 += t; else q1 += t;
+        }
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      if ((lane & 3) == 0) {
+        att[m * 16 + (lane >> 2)] = 1.f / (1.f + __expf(-(q0 + bpsi)));
+        att[m * 16 + (lane >> 2) + 8] = 1.f / (1.f + __expf(-(q1 + bpsi)));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CV; ++i) {
+      const int idx = lane + 32 * i, row = idx / CV, vec = (idx % CV) * 8;
+      const int64_t v = v0 + row;
+      if (v < total) {
+        float xv[8];
+        const uint4 raw = *reinterpret_cast<const uint4*>(tx + row * LD + vec);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        const float s = att[row];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xv[2 * j] = __uint_as_float(w[j] << 16) * s;
+          xv[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u) * s;
+        }
+        store8(op + v * a.out_cs + vec, xv);
+      }
+    }
+    if (a.psi_out && lane < 32 && v0 + lane < total)
+      static_cast<__nv_bfloat16*>(a.psi_out)[v0 + lane] = __float2bfloat16_rn(att[lane]);
+    __syncwarp();
+  }
+}
+
+template <int C>
+static int launch_gate_mma(const coma_gate_args& a, cudaStream_t stream) {
+  constexpr int F = C / 2, LD = C + 8;
+  const size_t smem = (size_t)(2 * F * LD + 8 * 2 * 32 * LD) * sizeof(__nv_bfloat16) + (size_t)(2 * F + 8 * 32) * sizeof(float);
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(gate_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  const int64_t ntiles = ((int64_t)a.B * a.V + 31) / 32;
+  const unsigned blocks = (unsigned)std::min<int64_t>((ntiles + 7) / 8, (int64_t)num_sms() * 2);
+  gate_mma_kernel<C><<<blocks, 256, smem, stream>>>(a);
+  COMA_CHECK_LAUNCH("gate_mma");
+  return COMA_OK;
+}
+
 template <typename T>
 static int launch_gate(const coma_gate_args& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.B * a.V;
@@ -140,7 +288,13 @@ extern "C" int coma_gate_fwd(const coma_gate_args* a, coma_stream_t stream) {
   COMA_CHECK_ARG(a->F * 2 == a->C, "coma_gate_fwd: F must be C/2");
   COMA_CHECK_ARG(a->g_cs % 8 == 0 && a->g_co % 8 == 0 && a->x_cs % 8 == 0 && a->x_co % 8 == 0 && a->out_cs % 8 == 0 &&
                      a->out_co % 8 == 0, "coma_gate_fwd: channel strides/offsets must be multiples of 8");
-  if (a->dtype == COMA_BF16) return launch_gate<__nv_bfloat16>(*a, stream);
+  if (a->dtype == COMA_BF16) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0;
+    if (aligned && a->C == 16) return launch_gate_mma<16>(*a, stream);
+    if (aligned && a->C == 32) return launch_gate_mma<32>(*a, stream);
+    if (aligned && a->C == 64) return launch_gate_mma<64>(*a, stream);
+    return launch_gate<__nv_bfloat16>(*a, stream);
+  }
   return launch_gate<float>(*a, stream);
 }
 
