@@ -233,6 +233,21 @@ def kernel_profile(step_fn, n=2):
             flops = conv_flops_of_call(name, a)
             tc = bool(_lib.lib().coma_conv3d_tcgen05_supported(cargs[0])) and a.impl != _lib.IMPL_SIMT
             shape = (a.B, a.Cin, a.Cout, a.Do, a.ksize, a.stride, a.transposed)
+        elif name in ("coma_gate_fwd", "coma_norm_film_act_fwd", "coma_gate_apply_fwd", "coma_roi_paint", "coma_pack2_fwd"):
+            a = cargs[0]._obj
+            es = 2 if a.dtype == _lib.BF16 else 4
+            vox = float(a.B) * float(a.V)
+            if name == "coma_gate_fwd":
+                nbytes = 3.0 * a.C * es * vox                      # read g, read x, write out
+            elif name == "coma_norm_film_act_fwd":
+                nbytes = (2.0 + (1.0 if a.r else 0.0)) * a.C * es * vox
+            elif name == "coma_gate_apply_fwd":
+                nbytes = (2.0 * a.C + 1.0) * es * vox
+            elif name == "coma_roi_paint":
+                nbytes = (8.0 + 4.0 + a.out_cs * es) * vox         # roi + mri (fp32) + prompt, write out_cs channels
+            else:
+                nbytes = (2.0 * es + a.dst_cs * es) * vox
+            shape = ("bytes", nbytes)
         elif name in ("coma_conv3d_wgrad", "coma_convT3d_wgrad"):
             a = cargs[0]._obj
             flops = 2.0 * a.B * a.Dg * a.Hg * a.Wg * a.ksize ** 3 * a.Cg * a.Cx
@@ -251,6 +266,7 @@ def kernel_profile(step_fn, n=2):
         _lib.call = orig
     fam = {}
     layers = []
+    hbm = {}
     for name, tc, flops, e0, e1, shape in records:
         ms = e0.elapsed_time(e1)
         key = name + (":tcgen05" if tc else "")
@@ -260,6 +276,14 @@ def kernel_profile(step_fn, n=2):
         f[2] += 1
         if flops:
             layers.append((key, shape, ms, flops))
+        if shape and shape[0] == "bytes":
+            h = hbm.setdefault(name, [0.0, 0.0, 0, 0.0])
+            h[0] += ms
+            h[1] += shape[1]
+            h[2] += 1
+            if shape[1] > 2.5e8:                      # launches big enough to be bandwidth- rather than latency-bound
+                h[3] = max(h[3], shape[1] / ms / 1e6)
+    kernel_profile.hbm = hbm
     return fam, layers
 
 
@@ -355,9 +379,14 @@ def run_ours(args):
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": None, "peak_source": peaks["source"], "launches_per_step": tc_n,
                 "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / max(total_ms, 1e-9)}
+    hbm_roof = {k: {"ms": v[0], "algorithmic_GB": v[1] / 1e9, "launches": v[2], "achieved_GBps": v[1] / v[0] / 1e6,
+                    "frac_of_measured_peak": v[1] / v[0] / 1e6 / peaks["hbm_gbs"],
+                    "best_large_launch_GBps": v[3], "best_large_launch_frac": v[3] / peaks["hbm_gbs"]}
+                for k, v in getattr(kernel_profile, "hbm", {}).items() if v[0] > 0}
     if rank == 0 and args.profile_out:
         with open(args.profile_out, "w") as f:
-            json.dump({"families": {k: {"ms": v[0], "gflop": v[1] / 1e9, "launches": v[2]} for k, v in fam.items()},
+            json.dump({"hbm_bound_kernels": hbm_roof,
+                       "families": {k: {"ms": v[0], "gflop": v[1] / 1e9, "launches": v[2]} for k, v in fam.items()},
                        "conv_layers": [{"kernel": k, "B,Cin,Cout,Do,k,stride,T": s, "ms": ms_, "tflops": fl / ms_ / 1e9}
                                        for k, s, ms_, fl in layers]}, f, indent=1)
 
@@ -377,7 +406,7 @@ def run_ours(args):
                        "channels": CHANNELS, "per_gpu_batch": batch, "parallelism": f"dp{world}",
                        "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
                        "model_tflops": value * gflop / 1e3, "model_frac_of_peak": value * gflop / 1e3 / peaks["tflops"]},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "roofline": roofline, "roofline_hbm_kernels": hbm_roof, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
         }

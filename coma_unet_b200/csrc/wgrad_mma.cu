@@ -5,6 +5,8 @@
 // Operands are staged voxel-major ([K][channels], the NDHWC layout as is) with cp.async (zero-fill outside the volume
 // = conv padding) and read with ldmatrix.trans.  This is the interim wgrad: the tcgen05 version (MN-major operands out
 // of the same halo slabs as the forward kernel) is described in DESIGN.md "next".
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace coma {
@@ -116,6 +118,136 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(coma_wgrad_args a, int64
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for 3x3x3 stride-1 layers with few channels (the 128^3 / 64^3 levels): the per-tap kernel above re-reads
+// g and x once per tap (27x) and is bound by that; here a CTA stages one 8x8x4 voxel block of g and the 10x10x6 halo
+// block of x in shared memory ONCE (cp.async, double buffered) and accumulates all 27 taps from it, one
+// [CgT x CxT] accumulator per tap held in registers across the whole persistent loop (27 x 4 registers per thread).
+// ------------------------------------------------------------------------------------------------
+constexpr int VW = 8, VH = 8, VD = 4, VOX = VW * VH * VD;                 // 256 output voxels per block step
+constexpr int XW = VW + 2, XH = VH + 2, XD = VD + 2, XROWS = XW * XH * XD;  // 600 halo voxels
+
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+
+template <int CGT, int CXT>
+__global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, int cx_tiles, int nbw, int nbh, int nbd) {
+  constexpr int LDG = CGT + 8, LDX = CXT + 8;
+  constexpr int MT = CGT / 16, NTL = CXT / 8, T = MT * NTL, WT_ = 8 / T;   // tiles, warps per tile (k split)
+  static_assert(T <= 8 && 8 % T == 0, "tile layout");
+  extern __shared__ __align__(16) uint8_t wsm[];
+  __nv_bfloat16* sg[2];
+  __nv_bfloat16* sx[2];
+  sg[0] = reinterpret_cast<__nv_bfloat16*>(wsm);
+  sx[0] = sg[0] + VOX * LDG;
+  sg[1] = sx[0] + XROWS * LDX;
+  sx[1] = sg[1] + VOX * LDG;
+
+  const int cg0 = (blockIdx.y / cx_tiles) * CGT, cx0 = (blockIdx.y % cx_tiles) * CXT;
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(a.g) + a.g_co + cg0;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(a.x) + a.x_co + cx0;
+  const int nblocks = a.B * nbd * nbh * nbw;
+
+  auto load_block = [&](int buf, int blk) {
+    int t = blk;
+    const int wb = t % nbw; t /= nbw;
+    const int hb = t % nbh; t /= nbh;
+    const int db = t % nbd; t /= nbd;
+    const int64_t b = t;
+    const int w0 = wb * VW, h0 = hb * VH, d0 = db * VD;
+    constexpr int GV = CGT / 8, XV = CXT / 8;
+    for (int i = threadIdx.x; i < VOX * GV; i += 256) {
+      const int row = i / GV, vec = (i % GV) * 8;
+      const int w = w0 + (row % VW), h = h0 + (row / VW) % VH, d = d0 + row / (VW * VH);
+      const bool ok = w < a.Wg && h < a.Hg && d < a.Dg;
+      const __nv_bfloat16* src = ok ? gp + (((b * a.Dg + d) * a.Hg + h) * a.Wg + w) * a.g_cs + vec : gp;
+      cp_async16(sg[buf] + row * LDG + vec, src, ok);
+    }
+    for (int i = threadIdx.x; i < XROWS * XV; i += 256) {
+      const int row = i / XV, vec = (i % XV) * 8;
+      const int w = w0 - 1 + (row % XW), h = h0 - 1 + (row / XW) % XH, d = d0 - 1 + row / (XW * XH);
+      const bool ok = w >= 0 && w < a.Wx && h >= 0 && h < a.Hx && d >= 0 && d < a.Dx;
+      const __nv_bfloat16* src = ok ? xp + (((b * a.Dx + d) * a.Hx + h) * a.Wx + w) * a.x_cs + vec : xp;
+      cp_async16(sx[buf] + row * LDX + vec, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = warp % T, kslice = warp / T;
+  const int m0 = (tile % MT) * 16, n0 = (tile / MT) * 8;
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+
+  int blk = blockIdx.x, it = 0;
+  if (blk < nblocks) load_block(0, blk);
+  for (; blk < nblocks; blk += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = blk + gridDim.x;
+    if (next < nblocks) {
+      load_block(buf ^ 1, next);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const __nv_bfloat16* g_s = sg[buf];
+    const __nv_bfloat16* x_s = sx[buf];
+#pragma unroll 1
+    for (int ks = kslice; ks < VOX / 16; ks += WT_) {
+      const int d = ks / (VH / 2), hp = ks % (VH / 2);           // 16 voxels = two h-lines (2hp, 2hp+1) of plane d
+      uint32_t af[4];
+      {
+        const int mat = lane >> 3, r = lane & 7;
+        ldsm_x4_t(af, g_s + ((d * VH + 2 * hp) * VW + (mat >> 1) * 8 + r) * LDG + m0 + (mat & 1) * 8);
+      }
+      const int lrow = ((lane >> 3) & 1) * XW + (lane & 7);      // second 8 voxels are the next h-line: +XW halo rows
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            uint32_t bf[2];
+            ldsm_x2_t(bf, x_s + (((d + kd) * XH + 2 * hp + kh) * XW + kw + lrow) * LDX + n0);
+            mma_bf16(acc[(kd * 3 + kh) * 3 + kw], af, bf[0], bf[1]);
+          }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int cg = cg0 + m0 + (lane >> 2) + (e >> 1) * 8;
+      const int cx = cx0 + n0 + (lane & 3) * 2 + (e & 1);
+      atomicAdd(a.dw + ((int64_t)t * a.Cg + cg) * a.Cx + cx, acc[t][e]);
+    }
+}
+
+template <int CGT, int CXT>
+int launch_wgrad_halo(const coma_wgrad_args& a, cudaStream_t stream) {
+  constexpr int LDG = CGT + 8, LDX = CXT + 8;
+  const size_t smem = (size_t)2 * (VOX * LDG + XROWS * LDX) * sizeof(__nv_bfloat16);
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(wgrad_halo_kernel<CGT, CXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  const int nbw = (a.Wg + VW - 1) / VW, nbh = (a.Hg + VH - 1) / VH, nbd = (a.Dg + VD - 1) / VD;
+  const int nblocks = a.B * nbw * nbh * nbd;
+  const int cg_tiles = a.Cg / CGT, cx_tiles = a.Cx / CXT;
+  int gx = num_sms() / (cg_tiles * cx_tiles);
+  if (gx < 1) gx = 1;
+  if (gx > nblocks) gx = nblocks;
+  dim3 grid((unsigned)gx, (unsigned)(cg_tiles * cx_tiles));
+  wgrad_halo_kernel<CGT, CXT><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
+  COMA_CHECK_LAUNCH("wgrad_halo");
+  return COMA_OK;
+}
 }  // namespace
 
 bool wgrad_mma_supported(const coma_wgrad_args& a) {
@@ -124,6 +256,15 @@ bool wgrad_mma_supported(const coma_wgrad_args& a) {
 }
 
 int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  static const bool halo_off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_HALO"); return e && e[0] == '1'; }();
+  if (!halo_off && a.ksize == 3 && a.stride == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && a.Cg <= 64 && a.Cx <= 64 &&
+      (int64_t)a.Dg * a.Hg * a.Wg >= 16 * 16 * 16) {
+    const bool g32 = a.Cg % 32 == 0, x32 = a.Cx % 32 == 0;
+    if (g32 && x32) return launch_wgrad_halo<32, 32>(a, stream);
+    if (g32) return launch_wgrad_halo<32, 16>(a, stream);
+    if (x32) return launch_wgrad_halo<16, 32>(a, stream);
+    return launch_wgrad_halo<16, 16>(a, stream);
+  }
   const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
   const int taps = a.ksize * a.ksize * a.ksize;
   const int cg_tiles = (a.Cg + WT - 1) / WT, cx_tiles = (a.Cx + WT - 1) / WT;

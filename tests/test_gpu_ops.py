@@ -54,6 +54,11 @@ CONV_CASES = [
     (2, 32, 16, 8, 8, 8, 1, 1, False),
     (2, 16, 1, 8, 8, 8, 1, 1, False),       # psi / head convs
     (1, 3, 5, 5, 6, 7, 3, 1, False),        # odd channel counts (scalar path)
+    # >= 16^3 voxels, k3 s1, <= 64 channels: halo weight-gradient kernel (bf16) / halo forward + dgrad kernels
+    (2, 16, 32, 16, 16, 16, 3, 1, False),
+    (1, 32, 32, 17, 18, 20, 3, 1, False),   # ragged in every dim
+    (1, 64, 32, 16, 16, 16, 3, 1, False),
+    (1, 16, 16, 12, 24, 16, 3, 1, False),
 ]
 
 
