@@ -142,7 +142,13 @@ def lib():
     return _lib
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream() -> int:
+    """Raw cudaStream_t of torch's current stream (the private fast accessor when available: this is on the per-launch path)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

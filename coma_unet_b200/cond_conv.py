@@ -25,6 +25,8 @@ FILM_HIDDEN = 64
 
 def covariate_matrix(covariate, like):
     """``[B,1,n]`` float32/float64 (VolumeDataset_ADNI_A4_combined.py:86) -> ``[B,n]`` float32 on x's device."""
+    if covariate.device == like.device and covariate.dtype == torch.float32:
+        return covariate.reshape(covariate.shape[0], -1)      # the model moved/cast it once per forward
     return covariate.reshape(covariate.shape[0], -1).to(device=like.device, dtype=torch.float32)
 
 

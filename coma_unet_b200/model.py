@@ -175,6 +175,8 @@ class ObservableAttentionUnet(nn.Module):
         return reduce_channels(d, covariate=covariate), encs, decs
 
     def forward(self, x, covariate=None):
+        if covariate is not None:
+            covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
         out, encs, decs = self._backbone(xv, covariate)
         to_user = lambda t: ops.vol_to_ncdhw(t).float()   # noqa: E731
@@ -280,7 +282,10 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         is_pos = (cov0 == 1).to(device=dev, dtype=torch.float32)
         used = (True, True)
         if torch.is_grad_enabled() and (self.pos_dynamic_prompt.requires_grad or self.neg_dynamic_prompt.requires_grad):
-            flags = (cov0 == 1).cpu()      # which prompts get a gradient at all (None otherwise, like the reference)
+            # which prompts get a gradient at all (None otherwise, like the reference's .item() branch, :638-639)
+            flags = getattr(self, "_host_flags", None)
+            if flags is None:
+                flags = (cov0 == 1).cpu()
             used = (bool(flags.any()), bool((~flags).any()))
         painted = ops.RoiPaintFn.apply(self.pos_dynamic_prompt, self.neg_dynamic_prompt, sample_roi_mask, x, lut,
                                        self._roi_ids, is_pos, self.PAD, dt, used)
@@ -291,8 +296,11 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         return self.final_pred_head(pair, final_relu=True)                             # conv1x1 + IN + PReLU, then ReLU
 
     def forward(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
-        if covariate is not None and x.device != covariate.device:
-            covariate = covariate.to(x.device)
+        self._host_flags = None
+        if covariate is not None:   # one H2D copy / cast per forward instead of one per conditioned layer
+            if not covariate.is_cuda:
+                self._host_flags = covariate.reshape(covariate.shape[0], -1)[:, 0] == 1     # no device sync needed
+            covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
         with blocks.bn_updates(2):   # the reference's duplicated backbone pass (:664,666) in closed form
             out, encoder_extractions, _ = self._backbone(xv, covariate)

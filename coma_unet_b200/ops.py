@@ -25,6 +25,8 @@ from . import _lib as L
 def vol_cs(t: torch.Tensor) -> int:
     """Voxel stride (elements) of an NDHWC tensor that may be a channel slice of a wider buffer."""
     assert t.dim() == 5, f"expected [B,D,H,W,C], got {tuple(t.shape)}"
+    if t.is_contiguous():
+        return t.shape[4]
     B, D, H, W, Cn = t.shape
     if Cn > 1:
         assert t.stride(4) == 1, "channels must be innermost"
