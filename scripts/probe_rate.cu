@@ -1,0 +1,114 @@
+// Throughput probe (one CTA): cycles per tcgen05.mma for small N in SS mode vs TS mode (A copied to TMEM with tcgen05.cp
+// once and reused by several MMAs), to decide whether the halo conv kernel should stage A through TMEM.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, int layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4); d |= (uint64_t)1 << 16; d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46; d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void cp256(uint32_t t, uint64_t a) { asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(t), "l"(a) : "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void body(bool leader, uint32_t tmem, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_hi, uint32_t b_hi,
+                                     uint32_t idesc, int N, int iters) {
+  for (int it = 0; it < iters / 18; ++it) {
+#pragma unroll
+    for (int u = 0; u < 18; ++u) {
+      const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(((u % 9) * 64 + (u % 3) * 640) >> 4));
+      const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)(((u % 8) * N * 64) >> 4));
+      if (leader) {
+        if (MODE == 0) {
+          mma_ss(tmem, ad, bd, idesc, 1);
+        } else if (MODE == 1) {
+          mma_ss(tmem + (uint32_t)((u % 3) * N), ad, bd, idesc, 1);
+        } else if (MODE == 2) {
+          if (u % 3 == 0) cp256(tmem + 448 + (uint32_t)(((u / 3) & 1) * 8), ad);
+          mma_ts(tmem + (uint32_t)((u % 3) * N), tmem + 448 + (uint32_t)(((u / 3) & 1) * 8), bd, idesc, 1);
+        } else if (MODE == 3) {
+          cp256(tmem + 448 + (uint32_t)((u & 1) * 8), ad);
+        } else if (MODE == 4) {
+          mma_ts(tmem + (uint32_t)((u % 3) * N), tmem + 448, bd, idesc, 1);
+        } else {
+          if (u % 6 == 0) cp256(tmem + 448 + (uint32_t)(((u / 6) & 1) * 8), ad);
+          mma_ts(tmem + (uint32_t)((u % 3) * N), tmem + 448 + (uint32_t)(((u / 6) & 1) * 8), bd, idesc, 1);
+        }
+      }
+    }
+  }
+}
+
+__global__ void rate(long long* out, int N, int iters) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f803f80u;
+  if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  if (threadIdx.x < 32) {
+    const bool leader = elect_one();
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32 * 1024);
+    const uint32_t a_hi = (640u >> 4) | (1u << 14) | (4u << 29), b_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+    const uint32_t a_lo0 = ((sa & 0x3FFFFu) >> 4) | 0x10000u, b_lo0 = ((sb & 0x3FFFFu) >> 4) | 0x10000u;
+    uint32_t parity = 0;
+#define RUN(M)                                                                                                   \
+    {                                                                                                            \
+      long long t0 = clock64();                                                                                  \
+      body<M>(leader, tmem, a_lo0, b_lo0, a_hi, b_hi, idesc, N, iters);                                          \
+      if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); \
+      __syncwarp();                                                                                              \
+      uint32_t done = 0;                                                                                         \
+      while (!done)                                                                                              \
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory"); \
+      parity ^= 1;                                                                                               \
+      if (leader) out[M] = clock64() - t0;                                                                       \
+    }
+    RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 64);
+  cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+  const char* names[6] = {"SS 1 acc", "SS 3 acc", "TS cp:mma 1:3", "cp only", "TS no cp", "TS cp:mma 1:6"};
+  for (int N : {16, 32, 64, 128}) {
+    const int iters = 5400;   // multiple of 18
+    rate<<<1, 128, 100 * 1024>>>(d, N, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    long long h[6]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("N=%3d:", N);
+    for (int m = 0; m < 6; ++m) printf("  %s %.1f cyc/op", names[m], (double)h[m] / iters);
+    printf("\n");
+  }
+  return 0;
+}
