@@ -619,6 +619,232 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 
 // ================================================================================================
+// v3: halo-reuse kernel with the kd taps fused into the MMA N dimension ("input-plane driven").
+//
+// Measured (profiles/r01_probe_mma_rate_ss_vs_ts.log): a 128 x N x 16 SS-mode MMA costs 40 / 48 / 64 cycles at
+// N = 32 / 64 / 128 -- the A-operand (activation) read from shared memory is the floor, so widening N is almost free.
+// An input plane p, shifted by (kh,kw), contributes to THREE output planes: p+1 through W[kd=0], p through W[kd=1],
+// p-1 through W[kd=2].  With the weight tiles stored [kh][kw][kd][co][ci], one MMA with N = 3*Cout and the same A
+// descriptor produces all three contributions into three neighbouring accumulator blocks of a TMEM ring
+// (8 blocks of Cout columns, block(d_out) = (-d_out) mod 8), i.e. a third of the A reads and MMA issues of v2.
+// The first contribution to an output plane is always its kd=0 block, issued separately with accumulate=0.
+// ================================================================================================
+constexpr int kRing = 8;
+
+template <int NT, int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;                                                   // 9 x [3 kd][NT][KC] weight tiles
+  uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
+  uint64_t* sempty = sfull + kMaxSlabs;
+  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + kRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kRing);
+  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < kRing; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w_bytes);
+      for (int t9 = 0; t9 < 9; ++t9)
+        for (int kd = 0; kd < 3; ++kd)
+          tma_load_2d(wreg + (size_t)(t9 * 3 + kd) * p.w_tile_bytes, &tmB, wfull, 0, (kd * 9 + t9) * p.Cout);
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int pi = 0; pi < sc.nd + 2; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          mbar_expect_tx(&sfull[slot], p.slab_tx);
+          tma_load_5d(slabs + (size_t)slot * p.slab_bytes, &tmA, &sfull[slot], 0, sc.w0 - 1, sc.h0 - 1, sc.d0 - 1 + pi, sc.b);
+          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (warp-uniform loop, one elected lane issues) ============
+    const bool leader = elect_one();
+    constexpr uint32_t ROWB = KC * 2u;
+    constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+    constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+    const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
+    const uint32_t slab16 = p.slab_bytes >> 4;
+    const uint32_t nslab = (uint32_t)p.nslab;
+    mbar_wait(wfull, 0);
+    uint32_t s = 0;            // ring block of the kd=0 target (output plane d0+pi) of the current input plane
+    uint32_t pbits = 0;        // per-block phase of tempty
+    uint32_t sslot = 0, sph = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      for (int pi = 0; pi < sc.nd + 2; ++pi) {
+        mbar_wait(&sfull[sslot], sph);
+        const int kd_lo = max(0, pi - sc.nd + 1), kd_hi = min(2, pi);
+        if (kd_lo == 0) {       // block s starts a new output plane: its previous tenant must have been drained
+          mbar_wait(&tempty[s], ((pbits >> s) & 1u) ^ 1u);
+          pbits ^= 1u << s;
+        }
+        tc_fence_after();
+        // runs of contiguous ring blocks: [ga .. ga+na) then (after the wrap) [0 .. nb)
+        auto make_run = [&](int k0, int k1, uint32_t& colA, uint32_t& nA, uint32_t& kA, uint32_t& nB, uint32_t& kB) {
+          const int n = k1 - k0 + 1;
+          const uint32_t slot_a = (s + (uint32_t)k0) & (kRing - 1);
+          colA = slot_a * NT; kA = (uint32_t)k0;
+          nA = n > 0 ? (uint32_t)min(n, (int)(kRing - slot_a)) : 0u;
+          nB = n > 0 ? (uint32_t)n - nA : 0u;
+          kB = (uint32_t)k0 + nA;
+        };
+        uint32_t colA, nA, kA, nB, kB;                  // general steps: all valid kd, accumulate
+        make_run(kd_lo, kd_hi, colA, nA, kA, nB, kB);
+        uint32_t colF, nF, kF, nG, kG;                  // first step: kd >= 1 part (kd = 0 goes alone with accumulate = 0)
+        make_run(max(kd_lo, 1), kd_hi, colF, nF, kF, nG, kG);
+        const uint32_t a_pl = s_lo + sslot * slab16;
+        auto mma = [&](uint32_t col, uint32_t nblk, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
+          const uint32_t idesc = IDESC0 | (((nblk * NT) >> 3) << 17);
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+              "setp.ne.b32 p, %6, 0;\n\t"
+              "mov.b64 da, {%1, %2};\n\t"
+              "mov.b64 db, {%3, %4};\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+              ::"r"(tmem_base + col), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(B_HI), "r"(idesc), "r"(accum)
+              : "memory");
+        };
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint32_t a_lo = a_pl + (uint32_t)((((t9 / 3) * HALO_W + (t9 % 3)) * ROWB + kk * 32u) >> 4);
+            const uint32_t b_t9 = w_lo + (uint32_t)(t9 * 3) * W_TILE16 + (uint32_t)(kk * 2);
+            if (leader) {
+              if (t9 == 0 && kk == 0 && kd_lo == 0) {
+                mma(s * NT, 1u, a_lo, b_t9, 0u);
+                if (nF) mma(colF, nF, a_lo, b_t9 + kF * W_TILE16, 1u);
+                if (nG) mma(0u, nG, a_lo, b_t9 + kG * W_TILE16, 1u);
+              } else {
+                mma(colA, nA, a_lo, b_t9 + kA * W_TILE16, 1u);
+                if (nB) mma(0u, nB, a_lo, b_t9 + kB * W_TILE16, 1u);
+              }
+            }
+          }
+        }
+        if (leader) {
+          if (pi >= 2) tc_commit(&tfull[(s + 2u) & (kRing - 1)]);   // output plane d0+pi-2 has all 27 taps
+          tc_commit(&sempty[sslot]);
+        }
+        __syncwarp();
+        if (++sslot == nslab) { sslot = 0; sph ^= 1u; }
+        s = (s + kRing - 1) & (kRing - 1);
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) =========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % HW_T, lh = row / HW_T;
+    const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    uint32_t s_seg = 0, ebits = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      const int oh = sc.h0 + lh, ow = sc.w0 + lw;
+      const bool valid = oh < p.H && ow < p.W;
+      float s1[NT], s2[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int i = 0; i < sc.nd; ++i) {
+        const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
+        __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs;
+        mbar_wait(&tfull[blk], (ebits >> blk) & 1u);
+        ebits ^= 1u << blk;
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t raw[16];
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+            if (!valid) v[j] = 0.f;
+            s1[c0 + j] += v[j];
+            s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
+          }
+          if (valid) {
+            if (p.scale) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
+            if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
+              uint4 lo, hi;
+              lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+              hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+              reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
+              reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[blk]);
+      }
+      s_seg = (s_seg + (uint32_t)(kRing * 64 - (sc.nd + 2))) & (kRing - 1);
+      if (p.stats) {
+        float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
+          if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
+          const float sm = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + (i >> 1)) * 2 + (i & 1)] = sm;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ================================================================================================
 // v2-T: halo-reuse kernel for the transposed convolution (k3, s2, p1, op1), Cin, Cout <= 64.
 // M tile = 8(w) x 16(h) voxels of one INPUT plane; the 9 x 17 slab of that plane (+1 halo on the high side) and of
 // the next plane serve all 27 taps; the 8 output-parity classes accumulate in 8 TMEM accumulators
@@ -906,7 +1132,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   h.slab_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
   h.w_tile_bytes = (uint32_t)a.Cout * h.rowb;
   h.w_bytes = 27u * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 4) * 8 + 16 + (size_t)4 * a.Cout * 2 * sizeof(float) + 64;
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)4 * a.Cout * 2 * sizeof(float) + 64;
   const size_t budget = 222 * 1024;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   if (fixed + 4 * (size_t)h.slab_bytes > budget) return h;
@@ -938,19 +1164,22 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
   p.stat_chunks = h.cols_w * h.cols_h * h.segs_d;
+  static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
   uint32_t cols = 32;
-  const uint32_t need = tr ? ((8u * NT * 2u <= 512u) ? 16u * NT : 8u * NT) : 2u * NT;
+  const uint32_t need = tr ? ((8u * NT * 2u <= 512u) ? 16u * NT : 8u * NT) : (v3 ? (uint32_t)kRing * NT : 2u * NT);
   while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   int grid = num_sms();
   if (grid > p.total_segs) grid = p.total_segs;
   if (tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else if (v3) conv_halo3_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
   return COMA_OK;
