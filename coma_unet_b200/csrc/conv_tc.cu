@@ -133,6 +133,62 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
   return d;
 }
 
+// ---------------------------------------------------------------------------------------------- epilogue helpers
+// y = act(cA[c] * acc + cS[c]) with cA = scale (or 1) and cS = scale*bias + shift staged in shared memory per (sample,
+// N tile); activation as hi + neg*lo (NONE: neg=1, RELU: neg=0, LEAKY/PReLU: neg=slope; clamp0 = ReLU(PReLU(.))).
+// The epilogue warps are the critical path once the MMA side is lean, so nothing but 1 FMA + 3 ALU ops per element remains.
+__device__ __forceinline__ void epi_stage_coef(const float* bias, const float* scale, const float* shift, int64_t bc_off, int n0,
+                                               int nt, float* cA, float* cS, int tid128) {
+  for (int j = tid128; j < nt; j += 128) {
+    const float a = scale ? __ldg(scale + bc_off + n0 + j) : 1.f;
+    const float bb = bias ? __ldg(bias + n0 + j) : 0.f;
+    cA[j] = a;
+    cS[j] = fmaf(a, bb, scale ? __ldg(shift + bc_off + n0 + j) : 0.f);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const float* cA, const float* cS, bool valid, float neg,
+                                            bool clamp0, float slope, bool stats, float* s1, float* s2,
+                                            __nv_bfloat16* yrow, int c_abs, int y_cn, int y_cs) {
+  float v[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 a = reinterpret_cast<const float4*>(cA)[q4], sh = reinterpret_cast<const float4*>(cS)[q4];
+    v[4 * q4 + 0] = fmaf(a.x, __uint_as_float(raw[4 * q4 + 0]), sh.x);
+    v[4 * q4 + 1] = fmaf(a.y, __uint_as_float(raw[4 * q4 + 1]), sh.y);
+    v[4 * q4 + 2] = fmaf(a.z, __uint_as_float(raw[4 * q4 + 2]), sh.z);
+    v[4 * q4 + 3] = fmaf(a.w, __uint_as_float(raw[4 * q4 + 3]), sh.w);
+  }
+  if (stats) {     // statistics are requested on the raw output (scale == NULL), so v is conv + bias here
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t = valid ? v[j] : 0.f;
+      s1[j] += t;
+      s2[j] = fmaf(t, t, s2[j]);
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float lo = fminf(v[j], 0.f), hi = fmaxf(v[j], 0.f);
+    v[j] = hi + (clamp0 ? fmaxf(slope * lo, 0.f) : neg * lo);
+  }
+  if (c_abs + 16 <= y_cn && (y_cs & 7) == 0) {
+    uint4 lo, hi;
+    lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+    hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+    reinterpret_cast<uint4*>(yrow)[0] = lo;
+    reinterpret_cast<uint4*>(yrow)[1] = hi;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c_abs + j < y_cn) yrow[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+__device__ __forceinline__ float act_neg(int act, float slope) { return act == COMA_ACT_NONE ? 1.f : (act == COMA_ACT_RELU ? 0.f : slope); }
+
 // taps of a tile: ordinary conv -> all k^3 taps; transposed conv -> the taps that hit output parity class `cls`
 struct Tap { int dd, dh, dw, widx; };
 __device__ __forceinline__ int num_taps(const TcParams& p, int cls) {
@@ -178,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][NT][2]
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));      // [4 warps][NT][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -282,7 +338,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;           // GEMM row = voxel inside the tile
     const int lw = row % TW, lh = (row / TW) % TH, ld = row / (TW * TH);
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const float neg = act_neg(p.act, slope);
+    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
     float* wstat = sstat + (size_t)(warp - 2) * p.NT * 2;
+    float* cA = sstat + 8 * p.NT;
+    float* cS = cA + p.NT;
     int local = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
       const TileCoord tc = decode_tile(p, t);
@@ -301,42 +361,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int n0 = tc.n_tile * p.NT;
       __nv_bfloat16* yrow = p.y + ((((int64_t)tc.b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.y_cs + n0;
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)tc.b * p.Cout, n0, p.NT, cA, cS, (int)threadIdx.x - 64);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       for (int c0 = 0; c0 < p.NT; c0 += 16) {
         uint32_t raw[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + c0), raw);
-        float v[16];
+        float s1c[16], s2c[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
-          if (!valid) v[j] = 0.f;
-        }
-        if (p.stats) {
+        for (int j = 0; j < 16; ++j) { s1c[j] = 0.f; s2c[j] = 0.f; }
+        epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+        if (do_stats) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float s1 = warp_sum(v[j]), s2 = warp_sum(v[j] * v[j]);
-            if (lane == 0) { wstat[(c0 + j) * 2] = s1; wstat[(c0 + j) * 2 + 1] = s2; }
-          }
-        }
-        if (valid) {
-          if (p.scale) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              v[j] = fmaf(__ldg(p.scale + (int64_t)tc.b * p.Cout + n0 + c0 + j), v[j], __ldg(p.shift + (int64_t)tc.b * p.Cout + n0 + c0 + j));
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
-          if (n0 + c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
-            uint4 lo, hi;
-            lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-            hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-            reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
-            reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
+            const float a1 = warp_sum(s1c[j]), a2 = warp_sum(s2c[j]);
+            if (lane == 0) { wstat[(c0 + j) * 2] = a1; wstat[(c0 + j) * 2 + 1] = a2; }
           }
         }
       }
@@ -344,6 +383,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (!p.stats) asm volatile("bar.sync 1, 128;" ::: "memory");   // coefficients of this tile are no longer read
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         // chunk index of this tile inside its sample
@@ -424,7 +464,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);                 // [4 warps][NT][2]
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));                 // [4 warps][NT][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -542,11 +582,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int lw = row % HW_T, lh = row / HW_T;
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const float neg = act_neg(p.act, slope);
+    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
+    float* cA = sstat + 8 * NT;
+    float* cS = cA + NT;
     int local = 0;
     for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
       const SegCoord sc = decode_seg(p, t);
       const int oh = sc.h0 + lh, ow = sc.w0 + lw;
       const bool valid = oh < p.H && ow < p.W;
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, (int)threadIdx.x - 64);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -559,39 +604,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), raw);
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-            if (!valid) v[j] = 0.f;
-            s1[c0 + j] += v[j];
-            s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
-          }
-          if (valid) {
-            if (p.scale) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
-            if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
-              uint4 lo, hi;
-              lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-              hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-              reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
-              reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
-            }
-          }
+          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps are done with this segment's coefficients
       if (p.stats) {   // one partial per segment: reduce the per-row running sums over the 128 rows
         float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
 #pragma unroll
@@ -644,7 +663,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + kRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kRing);
-  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -767,11 +786,16 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;
     const int lw = row % HW_T, lh = row / HW_T;
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const float neg = act_neg(p.act, slope);
+    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
+    float* cA = sstat + 8 * NT;
+    float* cS = cA + NT;
     uint32_t s_seg = 0, ebits = 0;
     for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
       const SegCoord sc = decode_seg(p, t);
       const int oh = sc.h0 + lh, ow = sc.w0 + lw;
       const bool valid = oh < p.H && ow < p.W;
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, (int)threadIdx.x - 64);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -785,40 +809,14 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-            if (!valid) v[j] = 0.f;
-            s1[c0 + j] += v[j];
-            s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
-          }
-          if (valid) {
-            if (p.scale) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
-            if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
-              uint4 lo, hi;
-              lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-              hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-              reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
-              reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
-            }
-          }
+          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[blk]);
       }
       s_seg = (s_seg + (uint32_t)(kRing * 64 - (sc.nd + 2))) & (kRing - 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps are done with this segment's coefficients
       if (p.stats) {
         float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
 #pragma unroll
@@ -867,7 +865,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sstat = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -984,12 +982,17 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;
     const int lw = row % HW_T, lh = row / HW_T;
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const float neg = act_neg(p.act, slope);
+    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
+    float* cA = sstat + 8 * NT;
+    float* cS = cA + NT;
     const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
     int local = 0;
     for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
       const SegCoord sc = decode_seg(p, t);
       const int ih = sc.h0 + lh, iw = sc.w0 + lw;
       const bool valid = ih < p.H && iw < p.W;
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, (int)threadIdx.x - 64);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -1006,40 +1009,14 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t raw[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 8 * NT + cls * NT + c0), raw);
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[j] = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-              if (!valid) v[j] = 0.f;
-              s1[c0 + j] += v[j];
-              s2[c0 + j] = fmaf(v[j], v[j], s2[c0 + j]);
-            }
-            if (valid) {
-              if (p.scale) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  v[j] = fmaf(__ldg(p.scale + (int64_t)sc.b * p.Cout + c0 + j), v[j], __ldg(p.shift + (int64_t)sc.b * p.Cout + c0 + j));
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = act_fwd(p.act, v[j], slope);
-              if (c0 + 16 <= p.y_cn && (p.y_cs & 7) == 0) {
-                uint4 lo, hi;
-                lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-                hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-                reinterpret_cast<uint4*>(yrow + c0)[0] = lo;
-                reinterpret_cast<uint4*>(yrow + c0)[1] = hi;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j < p.y_cn) yrow[c0 + j] = __float2bfloat16_rn(v[j]);
-              }
-            }
+            epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps are done with this segment's coefficients
       if (p.stats) {
         float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
 #pragma unroll
@@ -1132,7 +1109,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   h.slab_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
   h.w_tile_bytes = (uint32_t)a.Cout * h.rowb;
   h.w_bytes = 27u * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)4 * a.Cout * 2 * sizeof(float) + 64;
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * a.Cout * sizeof(float) + 64;
   const size_t budget = 222 * 1024;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   if (fixed + 4 * (size_t)h.slab_bytes > budget) return h;
@@ -1189,6 +1166,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 bool conv_tc_supported(const coma_conv_args& a) {
   if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
+  if (a.act == COMA_ACT_SIGMOID || (a.stats && a.scale)) return false;   // epilogue: relu-family activations; stats of the raw output
   if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;
   if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return false;
   if (a.transposed) return a.ksize == 3 && a.stride == 2;
@@ -1259,7 +1237,7 @@ int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
   while (cols < 2u * p.NT) cols <<= 1;
   p.tmem_cols = cols;
 
-  const size_t tail = 2 * kMaxStages * 8 + 4 * 8 + 16 + (size_t)4 * p.NT * 2 * sizeof(float) + 64;
+  const size_t tail = 2 * kMaxStages * 8 + 4 * 8 + 16 + (size_t)10 * p.NT * sizeof(float) + 64;
   const size_t budget = 200 * 1024;
   int stages = (int)((budget - tail - 1024) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
