@@ -650,6 +650,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 constexpr int kRing = 8;
 
+// All 27 taps of one input plane for the steady state (every kd valid) with the ring position S a compile-time
+// constant: every TMEM column, N and weight-tile offset is an immediate, so the single issuing warp spends ~8
+// instructions per MMA instead of ~40 (its instruction stream, not the tensor pipe, was the limit at small N).
+template <int NT, int KC, int S>
+__device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_base, uint32_t a_pl, uint32_t w_lo) {
+  constexpr uint32_t ROWB = KC * 2u;
+  constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+  constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+  constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+  constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
+  constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+  constexpr int nA = (3 < kRing - S) ? 3 : kRing - S, nB = 3 - nA;                 // kd 0..2 from block S (wraps at 8)
+  constexpr int SF = (S + 1) & (kRing - 1);
+  constexpr int nF = (2 < kRing - SF) ? 2 : kRing - SF, nG = 2 - nF;               // kd 1..2 from block S+1
+#define COMA_MMA(COL, NBLK, ALO, BLO, ACC)                                                                         \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\t"     \
+               "mov.b64 db, {%3, %4};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"             \
+               ::"r"(tmem_base + (uint32_t)(COL)), "r"(ALO), "r"(A_HI), "r"(BLO), "r"(B_HI),                       \
+                 "r"(IDESC0 | ((((uint32_t)(NBLK) * NT) >> 3) << 17)), "r"((uint32_t)(ACC)) : "memory")
+#pragma unroll
+  for (int t9 = 0; t9 < 9; ++t9) {
+#pragma unroll
+    for (int kk = 0; kk < KC / 16; ++kk) {
+      const uint32_t a_lo = a_pl + (uint32_t)((((t9 / 3) * HALO_W + (t9 % 3)) * ROWB + kk * 32u) >> 4);
+      const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3) * W_TILE16 + (uint32_t)(kk * 2);
+      if (leader) {
+        if (t9 == 0 && kk == 0) {
+          COMA_MMA(S * NT, 1, a_lo, b_lo, 0);
+          COMA_MMA(SF * NT, nF, a_lo, b_lo + W_TILE16, 1);
+          if (nG) COMA_MMA(0, nG, a_lo, b_lo + (1 + nF) * W_TILE16, 1);
+        } else {
+          COMA_MMA(S * NT, nA, a_lo, b_lo, 1);
+          if (nB) COMA_MMA(0, nB, a_lo, b_lo + nA * W_TILE16, 1);
+        }
+      }
+    }
+  }
+#undef COMA_MMA
+}
+
 template <int NT, int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
@@ -728,6 +768,27 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           pbits ^= 1u << s;
         }
         tc_fence_after();
+        if (kd_lo == 0 && kd_hi == 2) {       // steady state: dispatch on the ring position, everything else is immediates
+          const uint32_t a_pl0 = s_lo + sslot * slab16;
+          switch (s) {
+            case 0: halo3_issue_steady<NT, KC, 0>(leader, tmem_base, a_pl0, w_lo); break;
+            case 1: halo3_issue_steady<NT, KC, 1>(leader, tmem_base, a_pl0, w_lo); break;
+            case 2: halo3_issue_steady<NT, KC, 2>(leader, tmem_base, a_pl0, w_lo); break;
+            case 3: halo3_issue_steady<NT, KC, 3>(leader, tmem_base, a_pl0, w_lo); break;
+            case 4: halo3_issue_steady<NT, KC, 4>(leader, tmem_base, a_pl0, w_lo); break;
+            case 5: halo3_issue_steady<NT, KC, 5>(leader, tmem_base, a_pl0, w_lo); break;
+            case 6: halo3_issue_steady<NT, KC, 6>(leader, tmem_base, a_pl0, w_lo); break;
+            default: halo3_issue_steady<NT, KC, 7>(leader, tmem_base, a_pl0, w_lo); break;
+          }
+          if (leader) {
+            tc_commit(&tfull[(s + 2u) & (kRing - 1)]);
+            tc_commit(&sempty[sslot]);
+          }
+          __syncwarp();
+          if (++sslot == nslab) { sslot = 0; sph ^= 1u; }
+          s = (s + kRing - 1) & (kRing - 1);
+          continue;
+        }
         // runs of contiguous ring blocks: [ga .. ga+na) then (after the wrap) [0 .. nb)
         auto make_run = [&](int k0, int k1, uint32_t& colA, uint32_t& nA, uint32_t& kA, uint32_t& nB, uint32_t& kB) {
           const int n = k1 - k0 + 1;
