@@ -706,6 +706,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * NT;          // this CTA's slice of the output channels (Cout split when the weights do not fit)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
     mbar_init(wfull, 1);
@@ -729,7 +730,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_expect_tx(wfull, p.w_bytes);
       for (int t9 = 0; t9 < 9; ++t9)
         for (int kd = 0; kd < 3; ++kd)
-          tma_load_2d(wreg + (size_t)(t9 * 3 + kd) * p.w_tile_bytes, &tmB, wfull, 0, (kd * 9 + t9) * p.Cout);
+          tma_load_2d(wreg + (size_t)(t9 * 3 + kd) * p.w_tile_bytes, &tmB, wfull, 0, (kd * 9 + t9) * p.Cout + n0);
       uint32_t slot = 0, ph = 0;
       for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
         const SegCoord sc = decode_seg(p, t);
@@ -856,13 +857,13 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const SegCoord sc = decode_seg(p, t);
       const int oh = sc.h0 + lh, ow = sc.w0 + lw;
       const bool valid = oh < p.H && ow < p.W;
-      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, (int)threadIdx.x - 64);
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, (int)threadIdx.x - 64);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
       for (int i = 0; i < sc.nd; ++i) {
         const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
-        __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs;
+        __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs + n0;
         mbar_wait(&tfull[blk], (ebits >> blk) & 1u);
         ebits ^= 1u << blk;
         tc_fence_after();
@@ -870,7 +871,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
-          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
+          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
         }
         tc_fence_before();
         __syncwarp();
@@ -888,7 +889,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
           const float sm = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
-          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + (i >> 1)) * 2 + (i & 1)] = sm;
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -1155,7 +1156,7 @@ int pick_nt(int cout) {
 }
 
 // ---- halo-reuse (v2) planning ----
-struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab; uint32_t rowb, slab_bytes, w_tile_bytes, w_bytes; size_t smem; };
+struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, NT; uint32_t rowb, slab_bytes, w_tile_bytes, w_bytes; size_t smem; };
 
 HaloPlan plan_halo(const coma_conv_args& a) {
   HaloPlan h{};
@@ -1163,17 +1164,27 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   static const bool disabled = [] { const char* e = getenv("COMA_DISABLE_HALO"); return e && e[0] == '1'; }();
   if (disabled || a.ksize != 3) return h;
   if (a.transposed ? a.stride != 2 : a.stride != 1) return h;
-  if (!(a.Cin == 16 || a.Cin == 32 || a.Cin == 64) || !(a.Cout == 16 || a.Cout == 32 || a.Cout == 64)) return h;
+  if (!(a.Cin == 16 || a.Cin == 32 || a.Cin == 64) || a.Cout % 16 != 0 || a.Cout > 256) return h;
   const int gw = a.transposed ? a.Wi : a.Wo, gh = a.transposed ? a.Hi : a.Ho, gd = a.transposed ? a.Di : a.Do;
   if (gw < HW_T || gh < HH_T) return h;                  // tiny planes: the per-tap kernel wastes less
+  static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
   h.rowb = (uint32_t)a.Cin * 2u;
   h.slab_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
-  h.w_tile_bytes = (uint32_t)a.Cout * h.rowb;
-  h.w_bytes = 27u * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * a.Cout * sizeof(float) + 64;
   const size_t budget = 222 * 1024;
+  // N per CTA: all of Cout when the 27 weight tiles fit next to 4 slabs, otherwise (v3 only) split Cout over grid.y
+  h.NT = 0;
+  for (int nt : {64, 32, 16}) {
+    if (a.Cout % nt != 0) continue;
+    if (nt != a.Cout && (a.transposed || !v3)) continue;
+    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * nt * sizeof(float) + 64;
+    const size_t fixed_nt = 1024 + ((27u * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
+    if (fixed_nt + 4 * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
+  }
+  if (h.NT == 0) return h;
+  h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
+  h.w_bytes = 27u * h.w_tile_bytes;
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * h.NT * sizeof(float) + 64;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
-  if (fixed + 4 * (size_t)h.slab_bytes > budget) return h;
   int nslab = (int)((budget - fixed) / h.slab_bytes);
   h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
   h.smem = fixed + (size_t)h.nslab * h.slab_bytes;
@@ -1214,10 +1225,12 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
     cudaFuncSetAttribute(conv_halo3_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  int grid = num_sms();
+  const int nsplit = a.Cout / NT;
+  int grid = num_sms() / nsplit;
+  if (grid < 1) grid = 1;
   if (grid > p.total_segs) grid = p.total_segs;
   if (tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
-  else if (v3) conv_halo3_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else if (v3) conv_halo3_kernel<NT, KC><<<dim3((unsigned)grid, (unsigned)nsplit), kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
   return COMA_OK;
@@ -1262,11 +1275,11 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)27 * a.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)a.Cin, (cuuint32_t)a.Cout};
+    cuuint32_t box[2] = {(cuuint32_t)a.Cin, (cuuint32_t)h.NT};
     cuuint32_t estr[2] = {1, 1};
     if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
   }
-#define COMA_HALO_CASE(NTV, KCV) if (a.Cout == NTV && a.Cin == KCV) return launch_halo<NTV, KCV>(a, h, tmA, tmB, stream);
+#define COMA_HALO_CASE(NTV, KCV) if (h.NT == NTV && a.Cin == KCV) return launch_halo<NTV, KCV>(a, h, tmA, tmB, stream);
   COMA_HALO_CASE(16, 16) COMA_HALO_CASE(16, 32) COMA_HALO_CASE(16, 64)
   COMA_HALO_CASE(32, 16) COMA_HALO_CASE(32, 32) COMA_HALO_CASE(32, 64)
   COMA_HALO_CASE(64, 16) COMA_HALO_CASE(64, 32) COMA_HALO_CASE(64, 64)
