@@ -429,6 +429,7 @@ struct HaloParams {
   int cols_w, cols_h, segs_d, DS, total_segs;
   int nslab;
   uint32_t rowb, slab_bytes, slab_tx, w_tile_bytes, w_bytes;
+  uint32_t chunk_bytes, chunk_tx;   // per 64-channel chunk of a slab (v3 with Cin = 128: two chunks)
   __nv_bfloat16* y;
   int y_cs, y_cn;
   const float* bias; const float* scale; const float* shift; const float* slope;
@@ -650,39 +651,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 constexpr int kRing = 8;
 
-// All 27 taps of one input plane for the steady state (every kd valid) with the ring position S a compile-time
-// constant: every TMEM column, N and weight-tile offset is an immediate, so the single issuing warp spends ~8
-// instructions per MMA instead of ~40 (its instruction stream, not the tensor pipe, was the limit at small N).
-template <int NT, int KC, int S>
-__device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_base, uint32_t a_pl, uint32_t w_lo) {
+// All 27 taps of one input plane for the steady state (every kd valid).  The ring position S only matters through the
+// TMEM column of block S and through whether the three target blocks wrap around the ring (WRAP = 0: S <= 5, no wrap;
+// 1: S = 6; 2: S = 7), so three instantiations cover all eight positions; the tap loop stays rolled over (kh,kw) to keep
+// the single issuing warp's code inside the instruction cache (a fully unrolled 8-variant version thrashed it at Cin = 128).
+template <int NT, int KC, int KCH, int WRAP>
+__device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_base, uint32_t S, uint32_t a_pl, uint32_t w_lo, uint32_t chunk16) {
   constexpr uint32_t ROWB = KC * 2u;
   constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
   constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
   constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
   constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
   constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-  constexpr int nA = (3 < kRing - S) ? 3 : kRing - S, nB = 3 - nA;                 // kd 0..2 from block S (wraps at 8)
-  constexpr int SF = (S + 1) & (kRing - 1);
-  constexpr int nF = (2 < kRing - SF) ? 2 : kRing - SF, nG = 2 - nF;               // kd 1..2 from block S+1
-#define COMA_MMA(COL, NBLK, ALO, BLO, ACC)                                                                         \
+  constexpr int nA = 3 - WRAP, nB = WRAP;                         // kd 0..2 from block S: nA blocks, then nB from block 0
+  constexpr int nF = WRAP == 1 ? 1 : 2, nG = 2 - nF;              // kd 1..2 from block S+1 (S = 7: block 0, no wrap)
+  const uint32_t colS = tmem_base + S * NT;
+  const uint32_t colF = tmem_base + ((S + 1u) & (kRing - 1)) * NT;
+#define COMA_MMA(COLADDR, NBLK, ALO, BLO, ACC)                                                                     \
   asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\t"     \
                "mov.b64 db, {%3, %4};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"             \
-               ::"r"(tmem_base + (uint32_t)(COL)), "r"(ALO), "r"(A_HI), "r"(BLO), "r"(B_HI),                       \
+               ::"r"(COLADDR), "r"(ALO), "r"(A_HI), "r"(BLO), "r"(B_HI),                                           \
                  "r"(IDESC0 | ((((uint32_t)(NBLK) * NT) >> 3) << 17)), "r"((uint32_t)(ACC)) : "memory")
+  // first MMA of the plane: the kd = 0 block starts a new output plane (accumulate = 0), kd = 1,2 keep accumulating
+  if (leader) {
+    COMA_MMA(colS, 1, a_pl, w_lo, 0);
+    COMA_MMA(colF, nF, a_pl, w_lo + W_TILE16, 1);
+    if (nG) COMA_MMA(tmem_base, nG, a_pl, w_lo + (1 + nF) * W_TILE16, 1);
+  }
+  constexpr int UNROLL_KH = (KCH * (KC / 16) <= 2) ? 3 : 1;       // tiny bodies: unroll all 9 taps; big ones: keep the code small
+#pragma unroll UNROLL_KH
+  for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-  for (int t9 = 0; t9 < 9; ++t9) {
+    for (int kw = 0; kw < 3; ++kw) {
+      const uint32_t a_t9 = a_pl + (uint32_t)(kh * HALO_W + kw) * (ROWB >> 4);
+      const uint32_t b_t9 = w_lo + (uint32_t)((kh * 3 + kw) * KCH * 3) * W_TILE16;
 #pragma unroll
-    for (int kk = 0; kk < KC / 16; ++kk) {
-      const uint32_t a_lo = a_pl + (uint32_t)((((t9 / 3) * HALO_W + (t9 % 3)) * ROWB + kk * 32u) >> 4);
-      const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3) * W_TILE16 + (uint32_t)(kk * 2);
-      if (leader) {
-        if (t9 == 0 && kk == 0) {
-          COMA_MMA(S * NT, 1, a_lo, b_lo, 0);
-          COMA_MMA(SF * NT, nF, a_lo, b_lo + W_TILE16, 1);
-          if (nG) COMA_MMA(0, nG, a_lo, b_lo + (1 + nF) * W_TILE16, 1);
-        } else {
-          COMA_MMA(S * NT, nA, a_lo, b_lo, 1);
-          if (nB) COMA_MMA(0, nB, a_lo, b_lo + nA * W_TILE16, 1);
+      for (int kc = 0; kc < KCH; ++kc) {
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk) {
+          const uint32_t a_lo = a_t9 + (uint32_t)kc * chunk16 + (uint32_t)(kk * 2);
+          const uint32_t b_lo = b_t9 + (uint32_t)(kc * 3) * W_TILE16 + (uint32_t)(kk * 2);
+          if (leader && (kh | kw | kc | kk) != 0) {                // the very first MMA was issued above
+            COMA_MMA(colS, nA, a_lo, b_lo, 1);
+            if (nB) COMA_MMA(tmem_base, nB, a_lo, b_lo + nA * W_TILE16, 1);
+          }
         }
       }
     }
@@ -690,7 +702,7 @@ __device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_ba
 #undef COMA_MMA
 }
 
-template <int NT, int KC>
+template <int NT, int KC, int KCH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -729,15 +741,18 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       mbar_expect_tx(wfull, p.w_bytes);
       for (int t9 = 0; t9 < 9; ++t9)
-        for (int kd = 0; kd < 3; ++kd)
-          tma_load_2d(wreg + (size_t)(t9 * 3 + kd) * p.w_tile_bytes, &tmB, wfull, 0, (kd * 9 + t9) * p.Cout + n0);
+        for (int kc = 0; kc < KCH; ++kc)
+          for (int kd = 0; kd < 3; ++kd)
+            tma_load_2d(wreg + (size_t)((t9 * KCH + kc) * 3 + kd) * p.w_tile_bytes, &tmB, wfull, kc * KC, (kd * 9 + t9) * p.Cout + n0);
       uint32_t slot = 0, ph = 0;
       for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
         const SegCoord sc = decode_seg(p, t);
         for (int pi = 0; pi < sc.nd + 2; ++pi) {
           mbar_wait(&sempty[slot], ph ^ 1u);
           mbar_expect_tx(&sfull[slot], p.slab_tx);
-          tma_load_5d(slabs + (size_t)slot * p.slab_bytes, &tmA, &sfull[slot], 0, sc.w0 - 1, sc.h0 - 1, sc.d0 - 1 + pi, sc.b);
+          for (int kc = 0; kc < KCH; ++kc)
+            tma_load_5d(slabs + (size_t)slot * p.slab_bytes + (size_t)kc * p.chunk_bytes, &tmA, &sfull[slot], kc * KC, sc.w0 - 1, sc.h0 - 1,
+                        sc.d0 - 1 + pi, sc.b);
           if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
         }
       }
@@ -753,7 +768,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
     const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
-    const uint32_t slab16 = p.slab_bytes >> 4;
+    const uint32_t slab16 = p.slab_bytes >> 4, chunk16 = p.chunk_bytes >> 4;
     const uint32_t nslab = (uint32_t)p.nslab;
     mbar_wait(wfull, 0);
     uint32_t s = 0;            // ring block of the kd=0 target (output plane d0+pi) of the current input plane
@@ -771,16 +786,9 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         if (kd_lo == 0 && kd_hi == 2) {       // steady state: dispatch on the ring position, everything else is immediates
           const uint32_t a_pl0 = s_lo + sslot * slab16;
-          switch (s) {
-            case 0: halo3_issue_steady<NT, KC, 0>(leader, tmem_base, a_pl0, w_lo); break;
-            case 1: halo3_issue_steady<NT, KC, 1>(leader, tmem_base, a_pl0, w_lo); break;
-            case 2: halo3_issue_steady<NT, KC, 2>(leader, tmem_base, a_pl0, w_lo); break;
-            case 3: halo3_issue_steady<NT, KC, 3>(leader, tmem_base, a_pl0, w_lo); break;
-            case 4: halo3_issue_steady<NT, KC, 4>(leader, tmem_base, a_pl0, w_lo); break;
-            case 5: halo3_issue_steady<NT, KC, 5>(leader, tmem_base, a_pl0, w_lo); break;
-            case 6: halo3_issue_steady<NT, KC, 6>(leader, tmem_base, a_pl0, w_lo); break;
-            default: halo3_issue_steady<NT, KC, 7>(leader, tmem_base, a_pl0, w_lo); break;
-          }
+          if (s <= 5u) halo3_issue_steady<NT, KC, KCH, 0>(leader, tmem_base, s, a_pl0, w_lo, chunk16);
+          else if (s == 6u) halo3_issue_steady<NT, KC, KCH, 1>(leader, tmem_base, s, a_pl0, w_lo, chunk16);
+          else halo3_issue_steady<NT, KC, KCH, 2>(leader, tmem_base, s, a_pl0, w_lo, chunk16);
           if (leader) {
             tc_commit(&tfull[(s + 2u) & (kRing - 1)]);
             tc_commit(&sempty[sslot]);
@@ -818,11 +826,12 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int t9 = 0; t9 < 9; ++t9) {
 #pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk) {
-            const uint32_t a_lo = a_pl + (uint32_t)((((t9 / 3) * HALO_W + (t9 % 3)) * ROWB + kk * 32u) >> 4);
-            const uint32_t b_t9 = w_lo + (uint32_t)(t9 * 3) * W_TILE16 + (uint32_t)(kk * 2);
+          for (int kck = 0; kck < KCH * (KC / 16); ++kck) {
+            const int kc = kck / (KC / 16), kk = kck % (KC / 16);
+            const uint32_t a_lo = a_pl + (uint32_t)kc * chunk16 + (uint32_t)((((t9 / 3) * HALO_W + (t9 % 3)) * ROWB + kk * 32u) >> 4);
+            const uint32_t b_t9 = w_lo + (uint32_t)((t9 * KCH + kc) * 3) * W_TILE16 + (uint32_t)(kk * 2);
             if (leader) {
-              if (t9 == 0 && kk == 0 && kd_lo == 0) {
+              if (t9 == 0 && kck == 0 && kd_lo == 0) {
                 mma(s * NT, 1u, a_lo, b_t9, 0u);
                 if (nF) mma(colF, nF, a_lo, b_t9 + kF * W_TILE16, 1u);
                 if (nG) mma(0u, nG, a_lo, b_t9 + kG * W_TILE16, 1u);
@@ -1156,7 +1165,7 @@ int pick_nt(int cout) {
 }
 
 // ---- halo-reuse (v2) planning ----
-struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, NT; uint32_t rowb, slab_bytes, w_tile_bytes, w_bytes; size_t smem; };
+struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
 
 HaloPlan plan_halo(const coma_conv_args& a) {
   HaloPlan h{};
@@ -1164,25 +1173,32 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   static const bool disabled = [] { const char* e = getenv("COMA_DISABLE_HALO"); return e && e[0] == '1'; }();
   if (disabled || a.ksize != 3) return h;
   if (a.transposed ? a.stride != 2 : a.stride != 1) return h;
-  if (!(a.Cin == 16 || a.Cin == 32 || a.Cin == 64) || a.Cout % 16 != 0 || a.Cout > 256) return h;
+  static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
+  const bool use_v3 = v3 && !a.transposed;
+  const bool cin_ok = a.Cin == 16 || a.Cin == 32 || a.Cin == 64 || (use_v3 && a.Cin == 128);
+  if (!cin_ok || a.Cout % 16 != 0 || a.Cout > 256) return h;
   const int gw = a.transposed ? a.Wi : a.Wo, gh = a.transposed ? a.Hi : a.Ho, gd = a.transposed ? a.Di : a.Do;
   if (gw < HW_T || gh < HH_T) return h;                  // tiny planes: the per-tap kernel wastes less
-  static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
-  h.rowb = (uint32_t)a.Cin * 2u;
-  h.slab_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
+  h.KCH = a.Cin == 128 ? 2 : 1;
+  h.rowb = (uint32_t)(a.Cin / h.KCH) * 2u;
+  h.chunk_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
+  h.slab_bytes = h.chunk_bytes * (uint32_t)h.KCH;
   const size_t budget = 222 * 1024;
-  // N per CTA: all of Cout when the 27 weight tiles fit next to 4 slabs, otherwise (v3 only) split Cout over grid.y
+  // v2 / transposed keep three input planes live (+1 in flight); v3 consumes each plane once (+1 in flight)
+  const size_t min_slabs = use_v3 ? 2 : 4;
+  // N per CTA: all of Cout when the 27 weight tiles fit, otherwise (v3 only) split Cout over grid.y
   h.NT = 0;
   for (int nt : {64, 32, 16}) {
     if (a.Cout % nt != 0) continue;
-    if (nt != a.Cout && (a.transposed || !v3)) continue;
+    if (nt != a.Cout && !use_v3) continue;
     const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * nt * sizeof(float) + 64;
-    const size_t fixed_nt = 1024 + ((27u * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
-    if (fixed_nt + 4 * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
+    const size_t fixed_nt = 1024 + ((27u * h.KCH * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
+    if (fixed_nt + min_slabs * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
   }
   if (h.NT == 0) return h;
+  if (h.KCH > 1 && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
-  h.w_bytes = 27u * h.w_tile_bytes;
+  h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
   const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * h.NT * sizeof(float) + 64;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   int nslab = (int)((budget - fixed) / h.slab_bytes);
@@ -1201,14 +1217,15 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   return h;
 }
 
-template <int NT, int KC>
+template <int NT, int KC, int KCH = 1>
 int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
   HaloParams p{};
   const bool tr = a.transposed != 0;
-  p.B = a.B; p.D = tr ? a.Di : a.Do; p.H = tr ? a.Hi : a.Ho; p.W = tr ? a.Wi : a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = a.Cin;
+  p.B = a.B; p.D = tr ? a.Di : a.Do; p.H = tr ? a.Hi : a.Ho; p.W = tr ? a.Wi : a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = KC;
   p.cols_w = h.cols_w; p.cols_h = h.cols_h; p.segs_d = h.segs_d; p.DS = h.DS;
   p.total_segs = a.B * h.cols_w * h.cols_h * h.segs_d;
-  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb;
+  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb * (uint32_t)KCH;
+  p.chunk_bytes = h.chunk_bytes; p.chunk_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb;
   p.w_tile_bytes = h.w_tile_bytes; p.w_bytes = h.w_bytes;
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
@@ -1220,17 +1237,19 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (KCH == 1) {
+      cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int nsplit = a.Cout / NT;
   int grid = num_sms() / nsplit;
   if (grid < 1) grid = 1;
   if (grid > p.total_segs) grid = p.total_segs;
-  if (tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
-  else if (v3) conv_halo3_kernel<NT, KC><<<dim3((unsigned)grid, (unsigned)nsplit), kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  if (KCH == 1 && tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else if (v3 || KCH > 1) conv_halo3_kernel<NT, KC, KCH><<<dim3((unsigned)grid, (unsigned)nsplit), kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
   return COMA_OK;
@@ -1267,7 +1286,7 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
     cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
                              (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
-    cuuint32_t box[5] = {(cuuint32_t)a.Cin, (cuuint32_t)(a.transposed ? HT_W : HALO_W), (cuuint32_t)(a.transposed ? HT_H : HALO_H), 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(a.Cin / h.KCH), (cuuint32_t)(a.transposed ? HT_W : HALO_W), (cuuint32_t)(a.transposed ? HT_H : HALO_H), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
     if (!make_map(&tmA, base, 5, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
@@ -1275,7 +1294,7 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)27 * a.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)a.Cin, (cuuint32_t)h.NT};
+    cuuint32_t box[2] = {(cuuint32_t)(a.Cin / h.KCH), (cuuint32_t)h.NT};
     cuuint32_t estr[2] = {1, 1};
     if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
   }
@@ -1284,6 +1303,10 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
   COMA_HALO_CASE(32, 16) COMA_HALO_CASE(32, 32) COMA_HALO_CASE(32, 64)
   COMA_HALO_CASE(64, 16) COMA_HALO_CASE(64, 32) COMA_HALO_CASE(64, 64)
 #undef COMA_HALO_CASE
+  if (a.Cin == 128 && h.KCH == 2) {
+    if (h.NT == 16) return launch_halo<16, 64, 2>(a, h, tmA, tmB, stream);
+    if (h.NT == 32) return launch_halo<32, 64, 2>(a, h, tmA, tmB, stream);
+  }
   set_error("conv_halo: unsupported channel combination");
   return COMA_ERR_UNSUPPORTED;
 }

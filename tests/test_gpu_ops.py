@@ -351,6 +351,8 @@ TC_CASES = [
     (1, 64, 64, 6, 16, 16, 3, 1, False),     # weights do not fit: Cout split over grid.y (2 x 32)
     (1, 64, 128, 4, 16, 8, 3, 1, False),     # 4 x 32
     (2, 32, 128, 3, 32, 8, 3, 1, False),     # 2 x 64
+    (1, 128, 64, 5, 16, 16, 3, 1, False),    # Cin = 128: two 64-channel K chunks per slab, Cout split 4 x 16
+    (1, 128, 32, 3, 18, 9, 3, 1, False),
     # halo-reuse transposed kernel (8 parity classes in 8 TMEM accumulators)
     (2, 64, 32, 6, 16, 8, 3, 2, True),
     (1, 32, 16, 5, 20, 13, 3, 2, True),      # ragged
