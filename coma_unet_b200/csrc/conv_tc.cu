@@ -139,33 +139,47 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
 // The epilogue warps are the critical path once the MMA side is lean, so nothing but 1 FMA + 3 ALU ops per element remains.
 __device__ __forceinline__ void epi_stage_coef(const float* bias, const float* scale, const float* shift, int64_t bc_off, int n0,
                                                int nt, float* cA, float* cS, int tid128) {
+  float* cB = cS + nt;    // plain bias: the statistics are those of conv + bias, before any scale / shift
   for (int j = tid128; j < nt; j += 128) {
     const float a = scale ? __ldg(scale + bc_off + n0 + j) : 1.f;
     const float bb = bias ? __ldg(bias + n0 + j) : 0.f;
     cA[j] = a;
     cS[j] = fmaf(a, bb, scale ? __ldg(shift + bc_off + n0 + j) : 0.f);
+    cB[j] = bb;
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
-__device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const float* cA, const float* cS, bool valid, float neg,
-                                            bool clamp0, float slope, bool stats, float* s1, float* s2,
+// explicit shared-space 128-bit load (the coefficient pointers reach the epilogue as generic pointers, which compiled to LD.E)
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const float* cA, const float* cS, const float* cB, bool valid,
+                                            float neg, bool clamp0, float slope, bool stats, float* s1, float* s2,
                                             __nv_bfloat16* yrow, int c_abs, int y_cn, int y_cs) {
   float v[16];
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
-    const float4 a = reinterpret_cast<const float4*>(cA)[q4], sh = reinterpret_cast<const float4*>(cS)[q4];
+    const float4 a = lds128(cA + 4 * q4), sh = lds128(cS + 4 * q4);
     v[4 * q4 + 0] = fmaf(a.x, __uint_as_float(raw[4 * q4 + 0]), sh.x);
     v[4 * q4 + 1] = fmaf(a.y, __uint_as_float(raw[4 * q4 + 1]), sh.y);
     v[4 * q4 + 2] = fmaf(a.z, __uint_as_float(raw[4 * q4 + 2]), sh.z);
     v[4 * q4 + 3] = fmaf(a.w, __uint_as_float(raw[4 * q4 + 3]), sh.w);
   }
-  if (stats) {     // statistics are requested on the raw output (scale == NULL), so v is conv + bias here
+  if (stats) {     // statistics of conv + bias (the input of the following Instance/BatchNorm)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float t = valid ? v[j] : 0.f;
-      s1[j] += t;
-      s2[j] = fmaf(t, t, s2[j]);
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 bb = lds128(cB + 4 * q4);
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float t = valid ? __uint_as_float(raw[4 * q4 + e]) + bv[e] : 0.f;
+        s1[4 * q4 + e] += t;
+        s2[4 * q4 + e] = fmaf(t, t, s2[4 * q4 + e]);
+      }
     }
   }
   if (!valid) return;
@@ -370,7 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float s1c[16], s2c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1c[j] = 0.f; s2c[j] = 0.f; }
-        epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+        epi_chunk16(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
         if (do_stats) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -605,7 +619,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), raw);
-          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
+          epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
         }
         tc_fence_before();
         __syncwarp();
@@ -880,7 +894,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
-          epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+          epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
         }
         tc_fence_before();
         __syncwarp();
@@ -1080,7 +1094,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t raw[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 8 * NT + cls * NT + c0), raw);
-            epi_chunk16(raw, cA + c0, cS + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
+            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
           }
         }
         tc_fence_before();
@@ -1191,7 +1205,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   for (int nt : {64, 32, 16}) {
     if (a.Cout % nt != 0) continue;
     if (nt != a.Cout && !use_v3) continue;
-    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * nt * sizeof(float) + 64;
+    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)11 * nt * sizeof(float) + 64;
     const size_t fixed_nt = 1024 + ((27u * h.KCH * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
     if (fixed_nt + min_slabs * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
   }
@@ -1199,7 +1213,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   if (h.KCH > 1 && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
   h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)10 * h.NT * sizeof(float) + 64;
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)11 * h.NT * sizeof(float) + 64;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   int nslab = (int)((budget - fixed) / h.slab_bytes);
   h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
@@ -1259,7 +1273,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 bool conv_tc_supported(const coma_conv_args& a) {
   if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
-  if (a.act == COMA_ACT_SIGMOID || (a.stats && a.scale)) return false;   // epilogue: relu-family activations; stats of the raw output
+  if (a.act == COMA_ACT_SIGMOID) return false;   // epilogue: relu-family activations only
   if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;
   if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return false;
   if (a.transposed) return a.ksize == 3 && a.stride == 2;
@@ -1334,7 +1348,7 @@ int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
   while (cols < 2u * p.NT) cols <<= 1;
   p.tmem_cols = cols;
 
-  const size_t tail = 2 * kMaxStages * 8 + 4 * 8 + 16 + (size_t)10 * p.NT * sizeof(float) + 64;
+  const size_t tail = 2 * kMaxStages * 8 + 4 * 8 + 16 + (size_t)11 * p.NT * sizeof(float) + 64;
   const size_t budget = 200 * 1024;
   int stages = (int)((budget - tail - 1024) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

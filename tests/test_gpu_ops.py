@@ -378,7 +378,9 @@ def test_tcgen05_conv_matches_cuda_core_conv(case):
     outs = {}
     for impl in (L.IMPL_TCGEN05, L.IMPL_SIMT):
         y, st = ops.conv_raw(xv, wp, b, ksize=k, stride=s, transposed=tr, want_stats=True, impl=impl)
-        ye, _ = ops.conv_raw(xv, wp, b, ksize=k, stride=s, transposed=tr, scale=scale, shift=shift, act=L.ACT_RELU, impl=impl)
+        ye, ste = ops.conv_raw(xv, wp, b, ksize=k, stride=s, transposed=tr, scale=scale, shift=shift, act=L.ACT_RELU,
+                               want_stats=True, impl=impl)
+        assert err(ste.sum(dim=1), st.sum(dim=1)) < 1e-5      # statistics are those of conv + bias, whatever the epilogue
         outs[impl] = (y.float(), st.sum(dim=1), ye.float())
     yt, st_t, yet = outs[L.IMPL_TCGEN05]
     ys, st_s, yes = outs[L.IMPL_SIMT]
