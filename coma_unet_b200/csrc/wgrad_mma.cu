@@ -257,7 +257,7 @@ bool wgrad_mma_supported(const coma_wgrad_args& a) {
 
 int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream) {
   static const bool halo_off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_HALO"); return e && e[0] == '1'; }();
-  if (!halo_off && a.ksize == 3 && a.stride == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && a.Cg <= 64 && a.Cx <= 64 &&
+  if (!halo_off && a.ksize == 3 && a.stride == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && a.Cg <= 256 && a.Cx <= 256 &&
       (int64_t)a.Dg * a.Hg * a.Wg >= 16 * 16 * 16) {
     const bool g32 = a.Cg % 32 == 0, x32 = a.Cx % 32 == 0;
     if (g32 && x32) return launch_wgrad_halo<32, 32>(a, stream);

@@ -59,6 +59,7 @@ CONV_CASES = [
     (1, 32, 32, 17, 18, 20, 3, 1, False),   # ragged in every dim
     (1, 64, 32, 16, 16, 16, 3, 1, False),
     (1, 16, 16, 12, 24, 16, 3, 1, False),
+    (1, 64, 128, 16, 16, 16, 3, 1, False),  # halo wgrad tiled over 2 x 4 channel tiles
 ]
 
 
