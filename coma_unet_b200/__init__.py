@@ -9,7 +9,9 @@ from .criterions import GenerativeContrastiveLoss, RnCLoss, RoiMSE
 from .data import SyntheticVolumeDataset
 from .model import (AttentionLayer, ContrastiveAttentionUNET_DP, ObservableAttentionBlock, ObservableAttentionUnet,
                     ProjectionHead, StackedFusionConvLayers, UpBlock)
+from .parallel import DataParallelEngine
+from .train import train_dp
 
 __all__ = ["ContrastiveAttentionUNET_DP", "ObservableAttentionUnet", "AttentionLayer", "ObservableAttentionBlock",
            "UpBlock", "ProjectionHead", "StackedFusionConvLayers", "RoiMSE", "RnCLoss", "GenerativeContrastiveLoss",
-           "SyntheticVolumeDataset", "_lib"]
+           "SyntheticVolumeDataset", "DataParallelEngine", "train_dp", "_lib"]

@@ -152,3 +152,35 @@ def test_other_return_conventions_and_attention_dump(tmp_path):
         m.set_save_attn(None)
         x, e, d = cu.ObservableAttentionUnet.forward(m, mri, covars)
         assert x.shape == mri.shape and len(e) == 5 and len(d) == 4
+
+
+def test_train_loop_checkpoints_and_resumes(tmp_path):
+    """SURVEY 8(f) rank 1+2: the step loop, its checkpoint dict, and resuming from it."""
+    from torch.utils.data import DataLoader
+    from coma_unet_b200.train import train_dp
+    torch.manual_seed(0)
+    ds = cu.SyntheticVolumeDataset(length=3, shape=(32, 32, 32), seed=5)
+    index = {ds[i][4]: i for i in range(len(ds))}
+    roi_pred_fn = lambda paths: [ds.roi_predictions(index[p]) for p in paths]   # noqa: E731
+    loader = DataLoader(ds, batch_size=2)
+
+    def make():
+        m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5, conditional=True,
+                                           prompt_shape=(32, 32, 32), compute_dtype=torch.float32)
+        m.set_save_attn(None)
+        return common.fill_deterministic(m, 3).to(DEV)
+
+    m = make()
+    hist = train_dp(m, criterion(cu), loader, loader, epochs=2, lr=1e-3, save_path=str(tmp_path), cuda_id=0, roi_pred_fn=roi_pred_fn)
+    assert len(hist["epoch_avg_loss"]) == 2 and all(torch.isfinite(torch.tensor(hist["epoch_avg_loss"])))
+    assert hist["epoch_avg_loss"][1] < hist["epoch_avg_loss"][0]
+    ckpt = torch.load(tmp_path / "checkpoints" / "checkpoint_latest_epoch.pth", map_location="cpu")
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "scheduler_state_dict"} and ckpt["epoch"] == 1
+    # resume (validation.py:221-281 -> train_dp(from_checkpoint=True, optimizer=, scheduler=, start_epoch=))
+    m2 = make()
+    m2.load_state_dict(ckpt["model_state_dict"])
+    opt = torch.optim.AdamW(m2.parameters(), 1e-3)
+    opt.load_state_dict(ckpt["optimizer_state_dict"])
+    hist2 = train_dp(m2, criterion(cu), loader, None, epochs=3, lr=1e-3, save_path=str(tmp_path), cuda_id=0, from_checkpoint=True,
+                     optimizer=opt, scheduler=None, start_epoch=ckpt["epoch"] + 1, roi_pred_fn=roi_pred_fn)
+    assert len(hist2["epoch_avg_loss"]) == 1 and hist2["epoch_avg_loss"][0] < hist["epoch_avg_loss"][1] * 1.2
