@@ -138,7 +138,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
 // N tile); activation as hi + neg*lo (NONE: neg=1, RELU: neg=0, LEAKY/PReLU: neg=slope; clamp0 = ReLU(PReLU(.))).
 // The epilogue warps are the critical path once the MMA side is lean, so nothing but 1 FMA + 3 ALU ops per element remains.
 __device__ __forceinline__ void epi_stage_coef(const float* bias, const float* scale, const float* shift, int64_t bc_off, int n0,
-                                               int nt, float* cA, float* cS, int tid128) {
+                                               int nt, float* cA, float* cS, int tid128, uint32_t bar_id = 1u) {
   float* cB = cS + nt;    // plain bias: the statistics are those of conv + bias, before any scale / shift
   for (int j = tid128; j < nt; j += 128) {
     const float a = scale ? __ldg(scale + bc_off + n0 + j) : 1.f;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void epi_stage_coef(const float* bias, const float* s
     cS[j] = fmaf(a, bb, scale ? __ldg(shift + bc_off + n0 + j) : 0.f);
     cB[j] = bb;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
 // explicit shared-space 128-bit load (the coefficient pointers reach the epilogue as generic pointers, which compiled to LD.E)
@@ -716,8 +716,9 @@ __device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_ba
 #undef COMA_MMA
 }
 
-template <int NT, int KC, int KCH>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EPI epilogue warpgroups (4 warps each) drain alternate output planes: at N <= 32 the epilogue, not the MMA side, was the limit.
+template <int NT, int KC, int KCH, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -866,26 +867,35 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) =========================
+    // ================================ epilogue (warps 2..5 [, 6..9]) =========================
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                       // epilogue warpgroup: drains output planes with ocount % EPI == grp
+    const int tid128 = ((int)threadIdx.x - 64) & 127;
+    const uint32_t bar_id = 1u + (uint32_t)grp;
     const int row = q * 32 + lane;
     const int lw = row % HW_T, lh = row / HW_T;
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
     const float neg = act_neg(p.act, slope);
     const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
-    float* cA = sstat + 8 * NT;
+    float* gstat = sstat + (size_t)grp * 11 * NT;          // per group: [4 warps][NT][2] partial sums, then cA, cS, cB
+    float* cA = gstat + 8 * NT;
     float* cS = cA + NT;
+    uint32_t ocount = 0;
     uint32_t s_seg = 0, ebits = 0;
     for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
       const SegCoord sc = decode_seg(p, t);
       const int oh = sc.h0 + lh, ow = sc.w0 + lw;
       const bool valid = oh < p.H && ow < p.W;
-      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, (int)threadIdx.x - 64);
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, tid128, bar_id);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-      for (int i = 0; i < sc.nd; ++i) {
+      for (int i = 0; i < sc.nd; ++i, ++ocount) {
         const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
+        if (EPI > 1 && (ocount % EPI) != (uint32_t)grp) {    // the other warpgroup's plane: only track the barrier phase
+          ebits ^= 1u << blk;
+          continue;
+        }
         __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs + n0;
         mbar_wait(&tfull[blk], (ebits >> blk) & 1u);
         ebits ^= 1u << blk;
@@ -901,20 +911,20 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) mbar_arrive(&tempty[blk]);
       }
       s_seg = (s_seg + (uint32_t)(kRing * 64 - (sc.nd + 2))) & (kRing - 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps are done with this segment's coefficients
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // this group is done with the segment's coefficients
       if (p.stats) {
-        float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
+        float* wstat = gstat + (size_t)q * NT * 2;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
           if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
-          const float sm = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
-          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int i = tid128; i < NT * 2; i += 128) {
+          const float sm = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * EPI + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
     }
   }
@@ -1205,7 +1215,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   for (int nt : {64, 32, 16}) {
     if (a.Cout % nt != 0) continue;
     if (nt != a.Cout && !use_v3) continue;
-    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)11 * nt * sizeof(float) + 64;
+    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * nt * sizeof(float) + 64;
     const size_t fixed_nt = 1024 + ((27u * h.KCH * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
     if (fixed_nt + min_slabs * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
   }
@@ -1213,7 +1223,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   if (h.KCH > 1 && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
   h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)11 * h.NT * sizeof(float) + 64;
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   int nslab = (int)((budget - fixed) / h.slab_bytes);
   h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
@@ -1255,7 +1265,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
       cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
-    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int nsplit = a.Cout / NT;
@@ -1263,7 +1273,11 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   if (grid < 1) grid = 1;
   if (grid > p.total_segs) grid = p.total_segs;
   if (KCH == 1 && tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
-  else if (v3 || KCH > 1) conv_halo3_kernel<NT, KC, KCH><<<dim3((unsigned)grid, (unsigned)nsplit), kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else if (v3 || KCH > 1) {
+    constexpr int EPI = NT <= 32 ? 2 : 1;
+    p.stat_chunks *= EPI;
+    conv_halo3_kernel<NT, KC, KCH, EPI><<<dim3((unsigned)grid, (unsigned)nsplit), 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
+  }
   else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
   return COMA_OK;
@@ -1288,7 +1302,11 @@ static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int&
 
 int conv_tc_stat_chunks(const coma_conv_args& a) {
   const HaloPlan h = plan_halo(a);
-  if (h.ok) return h.cols_w * h.cols_h * h.segs_d;
+  if (h.ok) {
+    static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
+    const bool dual = !a.transposed && (v3 || h.KCH > 1) && h.NT <= 32;      // two epilogue warpgroups -> two partials per segment
+    return h.cols_w * h.cols_h * h.segs_d * (dual ? 2 : 1);
+  }
   int tw, th, td, cl;
   tile_counts(a, tw, th, td, cl);
   return tw * th * td * cl;
