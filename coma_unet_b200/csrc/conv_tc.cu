@@ -716,6 +716,75 @@ __device__ __forceinline__ void halo3_issue_steady(bool leader, uint32_t tmem_ba
 #undef COMA_MMA
 }
 
+// Epilogue shared by the plane-ring kernels (v3 and the stride-2 kernel): output plane i of a segment sits in ring block
+// (s_seg - i) mod 8 and the ring position advances by nd + SEG_EXTRA per segment (SEG_EXTRA = the extra input planes the
+// issuer steps through per segment: 2 for v3, 0 for stride 2, which counts output planes).
+template <int NT, int EPI, int SEG_EXTRA>
+__device__ __forceinline__ void ring_epilogue(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, float* sstat,
+                                              int n0, int warp, int lane) {
+  // ================================ epilogue (warps 2..5 [, 6..9]) =========================
+  const int q = warp & 3;
+  const int grp = (warp - 2) >> 2;                       // epilogue warpgroup: drains output planes with ocount % EPI == grp
+  const int tid128 = ((int)threadIdx.x - 64) & 127;
+  const uint32_t bar_id = 1u + (uint32_t)grp;
+  const int row = q * 32 + lane;
+  const int lw = row % HW_T, lh = row / HW_T;
+  const float slope = p.slope ? __ldg(p.slope) : 0.f;
+  const float neg = act_neg(p.act, slope);
+  const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
+  float* gstat = sstat + (size_t)grp * 11 * NT;          // per group: [4 warps][NT][2] partial sums, then cA, cS, cB
+  float* cA = gstat + 8 * NT;
+  float* cS = cA + NT;
+  uint32_t ocount = 0;
+  uint32_t s_seg = 0, ebits = 0;
+  for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+    const SegCoord sc = decode_seg(p, t);
+    const int oh = sc.h0 + lh, ow = sc.w0 + lw;
+    const bool valid = oh < p.H && ow < p.W;
+    epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, tid128, bar_id);
+    float s1[NT], s2[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (int i = 0; i < sc.nd; ++i, ++ocount) {
+      const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
+      if (EPI > 1 && (ocount % EPI) != (uint32_t)grp) {    // the other warpgroup's plane: only track the barrier phase
+        ebits ^= 1u << blk;
+        continue;
+      }
+      __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs + n0;
+      mbar_wait(&tfull[blk], (ebits >> blk) & 1u);
+      ebits ^= 1u << blk;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t raw[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
+        epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[blk]);
+    }
+    s_seg = (s_seg + (uint32_t)(kRing * 64 - (sc.nd + SEG_EXTRA))) & (kRing - 1);
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // this group is done with the segment's coefficients
+    if (p.stats) {
+      float* wstat = gstat + (size_t)q * NT * 2;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
+        if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      for (int i = tid128; i < NT * 2; i += 128) {
+        const float sm = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
+        p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * EPI + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    }
+  }
+
+}
+
 // EPI epilogue warpgroups (4 warps each) drain alternate output planes: at N <= 32 the epilogue, not the MMA side, was the limit.
 template <int NT, int KC, int KCH, int EPI>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
@@ -867,66 +936,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5 [, 6..9]) =========================
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;                       // epilogue warpgroup: drains output planes with ocount % EPI == grp
-    const int tid128 = ((int)threadIdx.x - 64) & 127;
-    const uint32_t bar_id = 1u + (uint32_t)grp;
-    const int row = q * 32 + lane;
-    const int lw = row % HW_T, lh = row / HW_T;
-    const float slope = p.slope ? __ldg(p.slope) : 0.f;
-    const float neg = act_neg(p.act, slope);
-    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
-    float* gstat = sstat + (size_t)grp * 11 * NT;          // per group: [4 warps][NT][2] partial sums, then cA, cS, cB
-    float* cA = gstat + 8 * NT;
-    float* cS = cA + NT;
-    uint32_t ocount = 0;
-    uint32_t s_seg = 0, ebits = 0;
-    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
-      const SegCoord sc = decode_seg(p, t);
-      const int oh = sc.h0 + lh, ow = sc.w0 + lw;
-      const bool valid = oh < p.H && ow < p.W;
-      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, tid128, bar_id);
-      float s1[NT], s2[NT];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-      for (int i = 0; i < sc.nd; ++i, ++ocount) {
-        const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
-        if (EPI > 1 && (ocount % EPI) != (uint32_t)grp) {    // the other warpgroup's plane: only track the barrier phase
-          ebits ^= 1u << blk;
-          continue;
-        }
-        __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + i)) * p.H + oh) * p.W + ow) * p.y_cs + n0;
-        mbar_wait(&tfull[blk], (ebits >> blk) & 1u);
-        ebits ^= 1u << blk;
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t raw[16];
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
-          epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[blk]);
-      }
-      s_seg = (s_seg + (uint32_t)(kRing * 64 - (sc.nd + 2))) & (kRing - 1);
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // this group is done with the segment's coefficients
-      if (p.stats) {
-        float* wstat = gstat + (size_t)q * NT * 2;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
-          if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        for (int i = tid128; i < NT * 2; i += 128) {
-          const float sm = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
-          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * EPI + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      }
-    }
+    ring_epilogue<NT, EPI, 2>(p, tmem_base, tfull, tempty, sstat, n0, warp, lane);
   }
 
   tc_fence_before();
@@ -1137,6 +1147,163 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ================================================================================================
+// v3-S2: plane-ring kernel for the stride-2 (k3, p1) down-sampling convolutions.
+// M tile = 8(w) x 16(h) OUTPUT voxels.  An input plane z is staged as four (h,w)-parity sub-slabs of 9 x 17 voxels
+// (TMA element strides 2 on W and H; sub-slab (ph,pw) starts at input (2 h0 - ph, 2 w0 - pw), out-of-range rows are
+// zero-filled = the padding), so tap kh reads parity ph = (kh != 1) at row shift (kh == 2), same along w: every tap
+// is again a row-shifted window of a resident slab.  Along depth the issuer walks input planes 2 d0 - 1 .. 2 d0 + 2 nd - 1:
+// an even plane 2 d feeds output d through kd = 1; an odd plane 2 d + 1 feeds output d + 1 through kd = 0 and output d
+// through kd = 2 with ONE MMA of N = 2 Cout (weight tiles stored [kh][kw][kd = 0, 2, 1], ring block(d) = (-d) mod 8),
+// so each plane is loaded and read once.
+// ================================================================================================
+constexpr int S2_ROWS = HT_ROWS;      // 9 x 17 voxels per parity sub-slab
+
+template <int NT, int KC, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, 1)
+conv_halo_s2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;                                                   // 9 x [kd = 0, 2, 1][NT][KC] weight tiles
+  uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
+  uint64_t* sempty = sfull + kMaxSlabs;
+  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + kRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kRing);
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * NT;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < kRing; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.w_bytes);
+      for (int t9 = 0; t9 < 9; ++t9)
+        for (int j = 0; j < 3; ++j) {
+          const int kd = j == 0 ? 0 : (j == 1 ? 2 : 1);
+          tma_load_2d(wreg + (size_t)(t9 * 3 + j) * p.w_tile_bytes, &tmB, wfull, 0, (kd * 9 + t9) * p.Cout + n0);
+        }
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int pi = 0; pi <= 2 * sc.nd; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          mbar_expect_tx(&sfull[slot], p.slab_tx);
+          for (int sub = 0; sub < 4; ++sub)
+            tma_load_5d(slabs + (size_t)slot * p.slab_bytes + (size_t)sub * p.chunk_bytes, &tmA, &sfull[slot], 0, 2 * sc.w0 - (sub & 1),
+                        2 * sc.h0 - (sub >> 1), 2 * sc.d0 - 1 + pi, sc.b);
+          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (warp-uniform loop, one elected lane issues) ============
+    const bool leader = elect_one();
+    constexpr uint32_t ROWB = KC * 2u;
+    constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+    constexpr uint32_t A_HI = ((HT_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t W_TILE16 = (NT * ROWB) >> 4;
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+    const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
+    const uint32_t slab16 = p.slab_bytes >> 4, sub16 = p.chunk_bytes >> 4;
+    const uint32_t nslab = (uint32_t)p.nslab;
+    mbar_wait(wfull, 0);
+    uint32_t s = 0;            // ring block of output plane d0 + pi/2 (the kd = 0 target of an odd input plane)
+    uint32_t pbits = 0;        // per-block phase of tempty
+    uint32_t sslot = 0, sph = 0;
+    auto mma = [&](uint32_t col, uint32_t nblk, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
+      const uint32_t idesc = IDESC0 | (((nblk * NT) >> 3) << 17);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, %6, 0;\n\t"
+          "mov.b64 da, {%1, %2};\n\t"
+          "mov.b64 db, {%3, %4};\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+          ::"r"(tmem_base + col), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(B_HI), "r"(idesc), "r"(accum)
+          : "memory");
+    };
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      for (int pi = 0; pi <= 2 * sc.nd; ++pi) {
+        mbar_wait(&sfull[sslot], sph);
+        const bool odd_plane = (pi & 1) == 0;               // input plane 2 d0 - 1 + pi
+        const bool has0 = odd_plane && pi < 2 * sc.nd;      // kd = 0 -> output pi/2 (block s) starts here
+        const bool has2 = odd_plane && pi > 0;              // kd = 2 -> output pi/2 - 1 (block s + 1)
+        if (has0) {
+          mbar_wait(&tempty[s], ((pbits >> s) & 1u) ^ 1u);
+          pbits ^= 1u << s;
+        }
+        tc_fence_after();
+        const uint32_t a_pl = s_lo + sslot * slab16;
+        const uint32_t col0 = s * NT, col2 = ((s + 1u) & (kRing - 1)) * NT;
+        const bool fused = has0 && has2 && s != (uint32_t)(kRing - 1);
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int kh = t9 / 3, kw = t9 % 3;
+          const int sub = (kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0);
+          const uint32_t a_t9 = a_pl + (uint32_t)sub * sub16 + (uint32_t)((((kh == 2 ? HT_W : 0) + (kw == 2 ? 1 : 0)) * ROWB) >> 4);
+          const uint32_t b_t9 = w_lo + (uint32_t)(t9 * 3) * W_TILE16;
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint32_t a_lo = a_t9 + (uint32_t)(kk * 2), b_lo = b_t9 + (uint32_t)(kk * 2);
+            if (leader) {
+              if (!odd_plane) {
+                mma(col2, 1u, a_lo, b_lo + 2u * W_TILE16, 1u);            // kd = 1 into output (pi-1)/2 = block s + 1
+              } else if (t9 == 0 && kk == 0) {
+                if (has0) mma(col0, 1u, a_lo, b_lo, 0u);                   // first contribution to a new output plane
+                if (has2) mma(col2, 1u, a_lo, b_lo + W_TILE16, 1u);
+              } else if (fused) {
+                mma(col0, 2u, a_lo, b_lo, 1u);
+              } else {
+                if (has0) mma(col0, 1u, a_lo, b_lo, 1u);
+                if (has2) mma(col2, 1u, a_lo, b_lo + W_TILE16, 1u);
+              }
+            }
+          }
+        }
+        if (leader) {
+          if (has2) tc_commit(&tfull[(s + 1u) & (kRing - 1)]);   // output pi/2 - 1 has all 27 taps
+          tc_commit(&sempty[sslot]);
+        }
+        __syncwarp();
+        if (++sslot == nslab) { sslot = 0; sph ^= 1u; }
+        if (has0) s = (s + kRing - 1) & (kRing - 1);   // the next odd plane starts the next output plane (also across segments)
+      }
+    }
+  } else {
+    ring_epilogue<NT, EPI, 0>(p, tmem_base, tfull, tempty, sstat, n0, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1189,24 +1356,26 @@ int pick_nt(int cout) {
 }
 
 // ---- halo-reuse (v2) planning ----
-struct HaloPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
+struct HaloPlan { bool ok, s2; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
 
 HaloPlan plan_halo(const coma_conv_args& a) {
   HaloPlan h{};
   h.ok = false;
   static const bool disabled = [] { const char* e = getenv("COMA_DISABLE_HALO"); return e && e[0] == '1'; }();
   if (disabled || a.ksize != 3) return h;
-  if (a.transposed ? a.stride != 2 : a.stride != 1) return h;
   static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
+  static const bool s2_off = [] { const char* e = getenv("COMA_DISABLE_HALO_S2"); return e && e[0] == '1'; }();
+  h.s2 = !a.transposed && a.stride == 2 && a.pad == 1 && v3 && !s2_off;
+  if (a.transposed ? a.stride != 2 : (a.stride != 1 && !h.s2)) return h;
   const bool use_v3 = v3 && !a.transposed;
-  const bool cin_ok = a.Cin == 16 || a.Cin == 32 || a.Cin == 64 || (use_v3 && a.Cin == 128);
+  const bool cin_ok = a.Cin == 16 || a.Cin == 32 || a.Cin == 64 || (use_v3 && !h.s2 && a.Cin == 128);
   if (!cin_ok || a.Cout % 16 != 0 || a.Cout > 256) return h;
   const int gw = a.transposed ? a.Wi : a.Wo, gh = a.transposed ? a.Hi : a.Ho, gd = a.transposed ? a.Di : a.Do;
   if (gw < HW_T || gh < HH_T) return h;                  // tiny planes: the per-tap kernel wastes less
   h.KCH = a.Cin == 128 ? 2 : 1;
   h.rowb = (uint32_t)(a.Cin / h.KCH) * 2u;
-  h.chunk_bytes = ((uint32_t)(a.transposed ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
-  h.slab_bytes = h.chunk_bytes * (uint32_t)h.KCH;
+  h.chunk_bytes = ((uint32_t)(a.transposed || h.s2 ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
+  h.slab_bytes = h.chunk_bytes * (uint32_t)(h.s2 ? 4 : h.KCH);      // stride 2: four (h,w)-parity sub-slabs per input plane
   const size_t budget = 222 * 1024;
   // v2 / transposed keep three input planes live (+1 in flight); v3 consumes each plane once (+1 in flight)
   const size_t min_slabs = use_v3 ? 2 : 4;
@@ -1220,7 +1389,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
     if (fixed_nt + min_slabs * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
   }
   if (h.NT == 0) return h;
-  if (h.KCH > 1 && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
+  if ((h.KCH > 1 || h.s2) && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
   h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
   const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
@@ -1248,7 +1417,8 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   p.B = a.B; p.D = tr ? a.Di : a.Do; p.H = tr ? a.Hi : a.Ho; p.W = tr ? a.Wi : a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = KC;
   p.cols_w = h.cols_w; p.cols_h = h.cols_h; p.segs_d = h.segs_d; p.DS = h.DS;
   p.total_segs = a.B * h.cols_w * h.cols_h * h.segs_d;
-  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes; p.slab_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb * (uint32_t)KCH;
+  p.nslab = h.nslab; p.rowb = h.rowb; p.slab_bytes = h.slab_bytes;
+  p.slab_tx = h.s2 ? 4u * (uint32_t)S2_ROWS * h.rowb : (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb * (uint32_t)KCH;
   p.chunk_bytes = h.chunk_bytes; p.chunk_tx = (uint32_t)(tr ? HT_ROWS : HALO_ROWS) * h.rowb;
   p.w_tile_bytes = h.w_tile_bytes; p.w_bytes = h.w_bytes;
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
@@ -1266,13 +1436,19 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
       cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (KCH == 1) cudaFuncSetAttribute(conv_halo_s2_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int nsplit = a.Cout / NT;
   int grid = num_sms() / nsplit;
   if (grid < 1) grid = 1;
   if (grid > p.total_segs) grid = p.total_segs;
-  if (KCH == 1 && tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  if (KCH == 1 && h.s2) {
+    constexpr int EPI = NT <= 32 ? 2 : 1;
+    p.stat_chunks *= EPI;
+    conv_halo_s2_kernel<NT, KC, EPI><<<dim3((unsigned)grid, (unsigned)nsplit), 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
+  }
+  else if (KCH == 1 && tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   else if (v3 || KCH > 1) {
     constexpr int EPI = NT <= 32 ? 2 : 1;
     p.stat_chunks *= EPI;
@@ -1318,8 +1494,10 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
     cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
                              (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
-    cuuint32_t box[5] = {(cuuint32_t)(a.Cin / h.KCH), (cuuint32_t)(a.transposed ? HT_W : HALO_W), (cuuint32_t)(a.transposed ? HT_H : HALO_H), 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t es = h.s2 ? 2 : 1;                // stride 2: one parity class per load (9 x 17 voxels out of an 18 x 34 window)
+    cuuint32_t box[5] = {(cuuint32_t)(a.Cin / h.KCH), (cuuint32_t)(a.transposed || h.s2 ? HT_W : HALO_W) * es,
+                         (cuuint32_t)(a.transposed || h.s2 ? HT_H : HALO_H) * es, 1, 1};
+    cuuint32_t estr[5] = {1, es, es, 1, 1};
     void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
     if (!make_map(&tmA, base, 5, dims, strides, box, estr, (int)h.rowb)) return COMA_ERR_CUDA;
   }

@@ -359,6 +359,12 @@ TC_CASES = [
     (1, 32, 16, 5, 20, 13, 3, 2, True),      # ragged
     (1, 64, 64, 4, 16, 16, 3, 2, True),      # single accumulator set (8 x 64 columns)
     (1, 16, 16, 9, 17, 9, 3, 2, True),
+    # stride-2 plane-ring kernel (parity sub-slabs; output planes >= 16 x 8)
+    (2, 32, 64, 16, 32, 16, 3, 2, False),    # one tile per output plane
+    (1, 64, 32, 11, 37, 19, 3, 2, False),    # odd input sizes, ragged tiles
+    (1, 16, 16, 20, 32, 34, 3, 2, False),    # 32B swizzle, two epilogue warpgroups
+    (1, 32, 128, 9, 32, 16, 3, 2, False),    # Cout split 2 x 64
+    (3, 32, 32, 40, 64, 32, 3, 2, False),    # many segments per CTA: ring wrap and phase bookkeeping
 ]
 
 
