@@ -6,7 +6,7 @@ Requires the in-tree CUDA library (coma_unet_b200/csrc/libcoma_b200.so); there i
 """
 from . import _lib
 from .criterions import GenerativeContrastiveLoss, RnCLoss, RoiMSE
-from .data import SyntheticVolumeDataset
+from .data import DevicePrefetcher, HostSink, SyntheticVolumeDataset
 from .model import (AttentionLayer, ContrastiveAttentionUNET_DP, ObservableAttentionBlock, ObservableAttentionUnet,
                     ProjectionHead, StackedFusionConvLayers, UpBlock)
 from .parallel import DataParallelEngine
@@ -14,4 +14,4 @@ from .train import train_dp
 
 __all__ = ["ContrastiveAttentionUNET_DP", "ObservableAttentionUnet", "AttentionLayer", "ObservableAttentionBlock",
            "UpBlock", "ProjectionHead", "StackedFusionConvLayers", "RoiMSE", "RnCLoss", "GenerativeContrastiveLoss",
-           "SyntheticVolumeDataset", "DataParallelEngine", "train_dp", "_lib"]
+           "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "_lib"]

@@ -956,8 +956,10 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ================================================================================================
 constexpr int HT_W = HW_T + 1, HT_H = HH_T + 1, HT_ROWS = HT_W * HT_H;
 
-template <int NT, int KC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EPI epilogue warpgroups split the 8 parity classes of every tile (group g drains classes with pd = g): the 8x larger output makes
+// the epilogue, not the MMA side, the limit of this kernel.
+template <int NT, int KC, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, 1)
 convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   constexpr int NACC = (8 * NT * 2 <= 512) ? 2 : 1;     // accumulator sets (8 classes each)
   extern __shared__ uint8_t smem_raw[];
@@ -976,7 +978,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
     mbar_init(wfull, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -1084,12 +1086,16 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int tid128 = ((int)threadIdx.x - 64) & 127;
+    const uint32_t bar_id = 1u + (uint32_t)grp;
     const int row = q * 32 + lane;
     const int lw = row % HW_T, lh = row / HW_T;
     const float slope = p.slope ? __ldg(p.slope) : 0.f;
     const float neg = act_neg(p.act, slope);
     const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
-    float* cA = sstat + 8 * NT;
+    float* gstat = sstat + (size_t)grp * 11 * NT;
+    float* cA = gstat + 8 * NT;
     float* cS = cA + NT;
     const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
     int local = 0;
@@ -1097,7 +1103,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const SegCoord sc = decode_seg(p, t);
       const int ih = sc.h0 + lh, iw = sc.w0 + lw;
       const bool valid = ih < p.H && iw < p.W;
-      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, (int)threadIdx.x - 64);
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, 0, NT, cA, cS, tid128, bar_id);
       float s1[NT], s2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -1107,7 +1113,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tfull[acc], par);
         tc_fence_after();
 #pragma unroll 1
-        for (int cls = 0; cls < 8; ++cls) {
+        for (int cls = grp * (8 / EPI); cls < (grp + 1) * (8 / EPI); ++cls) {
           const int od = 2 * (sc.d0 + i) + ((cls >> 2) & 1), oh = 2 * ih + ((cls >> 1) & 1), ow = 2 * iw + (cls & 1);
           __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * Do + od) * Ho + oh) * Wo + ow) * p.y_cs;
 #pragma unroll
@@ -1121,20 +1127,20 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps are done with this segment's coefficients
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // this group is done with the segment's coefficients
       if (p.stats) {
-        float* wstat = sstat + (size_t)(warp - 2) * NT * 2;
+        float* wstat = gstat + (size_t)q * NT * 2;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
           if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x - 64; i < NT * 2; i += 128) {
-          const float s = sstat[i] + sstat[NT * 2 + i] + sstat[NT * 4 + i] + sstat[NT * 6 + i];
-          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk) * p.Cout + (i >> 1)) * 2 + (i & 1)] = s;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int i = tid128; i < NT * 2; i += 128) {
+          const float s = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * EPI + grp) * p.Cout + (i >> 1)) * 2 + (i & 1)] = s;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
     }
   }
@@ -1433,7 +1439,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   if (!attr_set) {
     if (KCH == 1) {
       cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(convT_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(convT_halo_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (KCH == 1) cudaFuncSetAttribute(conv_halo_s2_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1448,7 +1454,11 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
     p.stat_chunks *= EPI;
     conv_halo_s2_kernel<NT, KC, EPI><<<dim3((unsigned)grid, (unsigned)nsplit), 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
   }
-  else if (KCH == 1 && tr) convT_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
+  else if (KCH == 1 && tr) {
+    constexpr int EPI = NT <= 32 ? 2 : 1;
+    p.stat_chunks *= EPI;
+    convT_halo_kernel<NT, KC, EPI><<<grid, 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
+  }
   else if (v3 || KCH > 1) {
     constexpr int EPI = NT <= 32 ? 2 : 1;
     p.stat_chunks *= EPI;
@@ -1480,7 +1490,7 @@ int conv_tc_stat_chunks(const coma_conv_args& a) {
   const HaloPlan h = plan_halo(a);
   if (h.ok) {
     static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
-    const bool dual = !a.transposed && (v3 || h.KCH > 1) && h.NT <= 32;      // two epilogue warpgroups -> two partials per segment
+    const bool dual = (a.transposed || v3 || h.KCH > 1) && h.NT <= 32;       // two epilogue warpgroups -> two partials per segment
     return h.cols_w * h.cols_h * h.segs_d * (dual ? 2 : 1);
   }
   int tw, th, td, cl;

@@ -52,3 +52,75 @@ class SyntheticVolumeDataset(Dataset):
         abeta = covars[0, 0].to(torch.float32)
         dev = self.device
         return (mri.to(dev), tau.to(dev), roi.to(dev), (abeta, covars), f"/synthetic/adni/{index:03d}-S-0000/PET/analysis/suvr.nii")
+
+
+class DevicePrefetcher:
+    """Device-side half of the reference's ``DataLoader(pin_memory=True)`` + ``.cuda(non_blocking=True)`` idiom
+    (attn_unet_data_parallel.py:795-812): iterates batches (tuples whose tensors live in pinned host memory), issues each
+    batch's host->device copies on a dedicated copy stream ``depth - 1`` batches ahead of the consumer, and hands out device
+    tensors that the consumer's current stream may use at once.  Non-tensor items pass through untouched.
+    """
+
+    def __init__(self, batches, device, depth=2):
+        self.batches, self.device, self.depth = batches, torch.device(device), max(1, depth)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _issue(self, batch):
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return dev, ready
+
+    def _hand_out(self, item):
+        dev, ready = item
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ready)
+        for t in dev:
+            if torch.is_tensor(t):
+                t.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
+        return dev
+
+    def __iter__(self):
+        from collections import deque
+        inflight = deque()
+        for batch in self.batches:
+            inflight.append(self._issue(batch))
+            if len(inflight) >= self.depth:
+                yield self._hand_out(inflight.popleft())
+        while inflight:
+            yield self._hand_out(inflight.popleft())
+
+
+class HostSink:
+    """Device->host read-back of per-step results into a small ring of pinned buffers on its own copy stream, so the
+    read of step i overlaps the compute of step i+1 (the reference reads ``pred.cpu()`` synchronously,
+    attn_unet_data_parallel.py:1226-1240).  ``put`` returns the pinned buffer that will hold the result once
+    ``wait()`` (or the buffer's next reuse) has returned."""
+
+    def __init__(self, shape, dtype=torch.float32, device="cuda", depth=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [torch.empty(tuple(shape), dtype=dtype).pin_memory() for _ in range(max(1, depth))]
+        self.done = [None] * len(self.bufs)
+        self.i = 0
+
+    def put(self, t):
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.done[i] is not None:
+            self.done[i].synchronize()              # the buffer's previous read-back (depth steps old) has landed
+        produced = torch.cuda.Event()
+        produced.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(produced)
+        with torch.cuda.stream(self.stream):
+            self.bufs[i].copy_(t.detach().reshape(self.bufs[i].shape), non_blocking=True)
+            t.record_stream(self.stream)
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.stream)
+        return self.bufs[i]
+
+    def wait(self):
+        for ev in self.done:
+            if ev is not None:
+                ev.synchronize()

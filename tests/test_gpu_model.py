@@ -184,3 +184,20 @@ def test_train_loop_checkpoints_and_resumes(tmp_path):
     hist2 = train_dp(m2, criterion(cu), loader, None, epochs=3, lr=1e-3, save_path=str(tmp_path), cuda_id=0, from_checkpoint=True,
                      optimizer=opt, scheduler=None, start_epoch=ckpt["epoch"] + 1, roi_pred_fn=roi_pred_fn)
     assert len(hist2["epoch_avg_loss"]) == 1 and hist2["epoch_avg_loss"][0] < hist["epoch_avg_loss"][1] * 1.2
+
+
+def test_prefetcher_and_sink_stream_batches_in_order():
+    """DevicePrefetcher / HostSink (the pinned DataLoader + non_blocking idiom): every batch arrives intact and in order
+    on the compute stream, and every result lands in host memory."""
+    host = [(torch.full((4, 1, 8, 8, 8), float(i)).pin_memory(), torch.arange(64.).pin_memory() + i, f"item{i}") for i in range(7)]
+    sink = cu.HostSink((4, 1, 8, 8, 8), torch.float32, "cuda", depth=2)
+    seen, results = [], []
+    for a, b, tag in cu.DevicePrefetcher(iter(host), "cuda", depth=3):
+        assert a.is_cuda and b.is_cuda and isinstance(tag, str)
+        seen.append(tag)
+        buf = sink.put(a * 2 + b[:1])
+        results.append(buf)
+    sink.wait()
+    assert seen == [f"item{i}" for i in range(7)]
+    # the ring holds the last `depth` results
+    assert float(results[-1][0, 0, 0, 0, 0]) == 2 * 6 + 6 and float(results[-2][0, 0, 0, 0, 0]) == 2 * 5 + 5
