@@ -54,6 +54,44 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+// streaming variants: read-once data, do not allocate in L1
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// raw (still packed) 8-element group: issue the loads of several groups first, unpack at the point of use
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { uint4 q[2]; };
+template <> struct Raw8<__nv_bfloat16> { uint4 q[1]; };
+__device__ __forceinline__ void ldraw_stream(const float* p, Raw8<float>& r) { r.q[0] = ldg_stream16(p); r.q[1] = ldg_stream16(p + 4); }
+__device__ __forceinline__ void ldraw_stream(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.q[0] = ldg_stream16(p); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = __uint_as_float(r.q[0].x); v[1] = __uint_as_float(r.q[0].y); v[2] = __uint_as_float(r.q[0].z); v[3] = __uint_as_float(r.q[0].w);
+  v[4] = __uint_as_float(r.q[1].x); v[5] = __uint_as_float(r.q[1].y); v[6] = __uint_as_float(r.q[1].z); v[7] = __uint_as_float(r.q[1].w);
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.q[0].x, r.q[0].y, r.q[0].z, r.q[0].w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void load8_stream(const float* p, float (&v)[8]) {
+  const uint4 a = ldg_stream16(p), b = ldg_stream16(p + 4);
+  v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+  v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+}
+__device__ __forceinline__ void load8_stream(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = ldg_stream16(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);

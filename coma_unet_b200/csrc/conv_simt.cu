@@ -5,6 +5,8 @@
 // `reduce_channels`, 1-channel heads), (3) on-device cross-check for the tensor-core kernels.
 // Replaces cuDNN fprop/dgrad/wgrad behind torch.nn.Conv3d / ConvTranspose3d
 // (reference call sites: attn_unet_data_parallel.py:126,285-306,442,495-497,546-558).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace coma {
@@ -145,9 +147,118 @@ static int launch_simt_t(const coma_conv_args& a, cudaStream_t stream) {
   return COMA_OK;
 }
 
-int conv_simt_stat_chunks(const coma_conv_args& a) { return simt_chunks(a); }
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise heads with one output channel (reduce_channels 32 -> 1 with per-sample expert-mixed weights, the 2 -> 1
+// final_pred_head, the projection heads): pure HBM streaming, so one thread walks many voxels with the weights in
+// registers and all loads of a voxel group in flight, instead of the generic one-voxel-per-thread gather above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPwThreads = 256;
+
+template <typename T, int CIN, bool VEC>
+__global__ void __launch_bounds__(kPwThreads) conv_pw1_kernel(coma_conv_args a, int chunks) {
+  // VEC: LPV = CIN/8 lanes share a voxel (16 bytes each), so a warp load covers 512 contiguous bytes; the partial dot
+  // products meet through shuffles.  Scalar path (tiny CIN): one lane per voxel.
+  constexpr int LPV = VEC ? CIN / 8 : 1, CPL = VEC ? 8 : CIN;       // lanes per voxel, channels per lane
+  constexpr int U = (VEC || CIN <= 4) ? 4 : 1;                      // voxels in flight per lane
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const int64_t per = (Vo + chunks - 1) / chunks;
+  const int64_t v0 = (int64_t)chunk * per, v1 = min(Vo, v0 + per);
+  const int part = threadIdx.x % LPV, vl = threadIdx.x / LPV;
+  constexpr int VPB = kPwThreads / LPV;                              // voxels per block and pass
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co + part * CPL;
+  const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride + part * CPL;
+  T* yb = static_cast<T*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co;
+  float w[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) w[c] = Elem<T>::ld(wb + c);
+  const float bias = a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride) : 0.f;
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const float sc = a.scale ? __ldg(a.scale + (int64_t)b * a.Cout) : 1.f, sh = a.scale ? __ldg(a.shift + (int64_t)b * a.Cout) : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t vb = v0 + vl; vb - vl < v1; vb += (int64_t)VPB * U) {      // warp-uniform trip count (shuffles inside)
+    float xv[U][CPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * VPB;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) xv[u][c] = 0.f;
+      if (v < v1) {
+        const T* xp = xb + v * a.x_cs;
+        if (VEC) {
+          float t8[8];
+          load8(xp, t8);
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) xv[u][c] = t8[c % 8];
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) xv[u][c] = Elem<T>::ld(xp + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * VPB;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc = fmaf(xv[u][c], w[c], acc);
+#pragma unroll
+      for (int o = 1; o < LPV; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (v < v1 && part == 0) {
+        const float val = acc + bias;
+        s1 += val;
+        s2 = fmaf(val, val, s2);
+        Elem<T>::st(yb + v * a.y_cs, act_fwd(a.act, fmaf(sc, val, sh), slope));
+      }
+    }
+  }
+  if (a.stats) {
+    __shared__ float red[kPwThreads / 32][2];
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s1; red[threadIdx.x >> 5][1] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < kPwThreads / 32; ++wi) t += red[wi][threadIdx.x];
+      a.stats[((int64_t)b * chunks + chunk) * 2 + threadIdx.x] = t;
+    }
+  }
+}
+
+static bool pw1_applicable(const coma_conv_args& a) {
+  return a.ksize == 1 && a.stride == 1 && !a.transposed && a.Cout == 1 && a.y_cn >= 1 &&
+         (a.Cin == 1 || a.Cin == 2 || a.Cin == 3 || a.Cin == 8 || a.Cin == 16 || a.Cin == 32 || a.Cin == 64);
+}
+static int pw1_chunks(const coma_conv_args& a) {
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const int64_t by_work = (Vo + kPwThreads * 8 - 1) / (kPwThreads * 8);
+  const int64_t by_sms = (8 * (int64_t)num_sms() + a.B - 1) / a.B;
+  return (int)std::max<int64_t>(1, std::min(by_work, by_sms));
+}
+
+template <typename T>
+static int launch_pw1_t(const coma_conv_args& a, cudaStream_t stream) {
+  const int chunks = pw1_chunks(a);
+  const bool vec = (a.Cin % 8 == 0) && (a.x_cs % 8 == 0) && (a.x_co % 8 == 0) && (reinterpret_cast<uintptr_t>(a.x) % 32 == 0);
+  dim3 grid((unsigned)chunks, (unsigned)a.B);
+#define COMA_PW_CASE(C)                                                                                 \
+  if (a.Cin == C) {                                                                                     \
+    if (vec && C % 8 == 0) conv_pw1_kernel<T, C, (C % 8 == 0)><<<grid, kPwThreads, 0, stream>>>(a, chunks); \
+    else conv_pw1_kernel<T, C, false><<<grid, kPwThreads, 0, stream>>>(a, chunks);                      \
+  }
+  COMA_PW_CASE(1) COMA_PW_CASE(2) COMA_PW_CASE(3) COMA_PW_CASE(8) COMA_PW_CASE(16) COMA_PW_CASE(32) COMA_PW_CASE(64)
+#undef COMA_PW_CASE
+  COMA_CHECK_LAUNCH("conv_pw1");
+  return COMA_OK;
+}
+
+int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : simt_chunks(a); }
 
 int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
+  if (pw1_applicable(a)) return a.dtype == COMA_BF16 ? launch_pw1_t<__nv_bfloat16>(a, stream) : launch_pw1_t<float>(a, stream);
   if (a.dtype == COMA_BF16) return launch_simt_t<__nv_bfloat16>(a, stream);
   return launch_simt_t<float>(a, stream);
 }

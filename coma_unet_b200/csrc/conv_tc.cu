@@ -192,8 +192,14 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const flo
     uint4 lo, hi;
     lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
     hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-    reinterpret_cast<uint4*>(yrow)[0] = lo;
-    reinterpret_cast<uint4*>(yrow)[1] = hi;
+    if ((reinterpret_cast<uintptr_t>(yrow) & 31) == 0) {
+      // one 256-bit store = one full 32-byte sector per voxel (two 128-bit stores cost the LSU two half-sector writes)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"l"(yrow), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    } else {
+      reinterpret_cast<uint4*>(yrow)[0] = lo;
+      reinterpret_cast<uint4*>(yrow)[1] = hi;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)

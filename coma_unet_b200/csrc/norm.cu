@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(coma_norm_finalize_a
 }
 
 // ---- apply: y = act(A*x + S) ---------------------------------------------------------------------
-template <typename T>
+// SIMPLE: act in {none, relu, leaky/prelu} evaluated as max(u,0) + neg * min(u,0) (no per-element dispatch on the act code)
+template <typename T, int U, bool SIMPLE, bool HASR>
 __global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_act_args a, int chunks) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int CV = a.C >> 3, lanes = kThreads / CV;
@@ -253,16 +254,36 @@ __global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_ac
     S8[e] = a.S[(int64_t)b * a.C + cvec * 8 + e];
   }
   const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const float neg = a.act == COMA_ACT_NONE ? 1.f : (a.act == COMA_ACT_RELU ? 0.f : slope);
   const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co + cvec * 8;
   T* yb = static_cast<T*>(a.y) + (int64_t)b * a.V * a.y_cs + a.y_co + cvec * 8;
-  const T* rb = a.r ? static_cast<const T*>(a.r) + (int64_t)b * a.V * a.r_cs + cvec * 8 : nullptr;
-  for (int64_t v = v0 + vlane; v < v1; v += lanes) {
-    float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    load8(xb + v * a.x_cs, xv);
-    if (rb) load8(rb + v * a.r_cs, rv);
+  const T* rb = HASR ? static_cast<const T*>(a.r) + (int64_t)b * a.V * a.r_cs + cvec * 8 : nullptr;
+  // four voxels per thread and iteration, every load issued before the first use: HBM streaming wants bytes in flight
+  for (int64_t vb = v0 + vlane; vb < v1; vb += (int64_t)lanes * U) {
+    Raw8<T> xr[U], rr[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) xv[e] = act_fwd(a.act, fmaf(A8[e], xv[e], S8[e]) + rv[e], slope);
-    store8(yb + v * a.y_cs, xv);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * lanes;
+      if (v < v1) {
+        ldraw_stream(xb + v * a.x_cs, xr[u]);
+        if (HASR) ldraw_stream(rb + v * a.r_cs, rr[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * lanes;
+      if (v < v1) {
+        float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unpack8(xr[u], xv);
+        if (HASR) unpack8(rr[u], rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float u = HASR ? fmaf(A8[e], xv[e], S8[e]) + rv[e] : fmaf(A8[e], xv[e], S8[e]);
+          xv[e] = SIMPLE ? fmaf(neg, fminf(u, 0.f), fmaxf(u, 0.f)) : act_fwd(a.act, u, slope);
+        }
+        store8(yb + v * a.y_cs, xv);
+      }
+    }
   }
 }
 
@@ -434,10 +455,21 @@ extern "C" int coma_norm_film_act_fwd(const coma_affine_act_args* a, coma_stream
   const bool vec = vec_ok(a->x, a->C, a->x_cs, a->x_co, a->dtype) && vec_ok(a->y, a->C, a->y_cs, a->y_co, a->dtype) &&
                    (!a->r || vec_ok(a->r, a->C, a->r_cs, 0, a->dtype));
   if (vec) {
-    const int chunks = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
+    static const int env_chunks = [] { const char* e = getenv("COMA_AFFINE_CHUNKS"); return e ? atoi(e) : 0; }();
+    int chunks = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
+    if (env_chunks > 0) chunks = env_chunks;
     dim3 grid((unsigned)chunks, (unsigned)a->B);
-    if (a->dtype == COMA_BF16) affine_act_vec_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a, chunks);
-    else affine_act_vec_kernel<float><<<grid, kThreads, 0, stream>>>(*a, chunks);
+    const bool simple = a->act == COMA_ACT_NONE || a->act == COMA_ACT_RELU || a->act == COMA_ACT_LEAKY;
+#define COMA_AFFINE_LAUNCH(T, U)                                                                                     \
+    do {                                                                                                              \
+      if (simple && !a->r) affine_act_vec_kernel<T, U, true, false><<<grid, kThreads, 0, stream>>>(*a, chunks);       \
+      else if (simple) affine_act_vec_kernel<T, U, true, true><<<grid, kThreads, 0, stream>>>(*a, chunks);            \
+      else if (!a->r) affine_act_vec_kernel<T, U, false, false><<<grid, kThreads, 0, stream>>>(*a, chunks);           \
+      else affine_act_vec_kernel<T, U, false, true><<<grid, kThreads, 0, stream>>>(*a, chunks);                       \
+    } while (0)
+    if (a->dtype == COMA_BF16) COMA_AFFINE_LAUNCH(__nv_bfloat16, 2);
+    else COMA_AFFINE_LAUNCH(float, 1);
+#undef COMA_AFFINE_LAUNCH
   } else {
     COMA_CHECK_ARG(a->C <= 64, "coma_norm_film_act_fwd: unaligned C=%d too large for the scalar path", a->C);
     dim3 grid((unsigned)std::min<int64_t>((a->V + kThreads - 1) / kThreads, 2048), (unsigned)a->B);

@@ -3,6 +3,8 @@
 //                       forward_modulator_with_uq (attn_unet_data_parallel.py:632-649)
 //  - coma_pack2_*       replace `general_prompt + ...` and the torch.cat calls (:651,654)
 //  - coma_roi_mse_*     replace RoiMSE.forward (criterions.py:181-211; ~40 ATen kernels + 2 syncs)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace coma {
@@ -62,24 +64,38 @@ __global__ void __launch_bounds__(256) roi_paint_bwd_kernel(const T* __restrict_
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack2_kernel(coma_pack2_args a) {
-  const int64_t total = (int64_t)a.B * a.V;
-  const T* pa = static_cast<const T*>(a.a);
-  const T* pb = static_cast<const T*>(a.b);
-  T* d = static_cast<T*>(a.dst);
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int64_t v = i % a.V;
-    T* o = d + i * a.dst_cs;
-    const float va = Elem<T>::ld(pa + i) + (a.a_add ? __ldg(a.a_add + v) : 0.f);
-    const float vb = pb ? Elem<T>::ld(pb + i) : 0.f;
-    if ((a.dst_cs & 7) == 0) {
-      float vals[8] = {va, vb, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      store8(o, vals);
-      const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int c = 8; c < a.dst_cs; c += 8) store8(o + c, zeros);
-    } else {
-      Elem<T>::st(o, va);
-      Elem<T>::st(o + 1, vb);
-      for (int c = 2; c < a.dst_cs; ++c) Elem<T>::st(o + c, 0.f);
+  const int b = blockIdx.y;                       // one sample per grid row: no 64-bit modulo per voxel
+  const T* pa = static_cast<const T*>(a.a) + (int64_t)b * a.V;
+  const T* pb = a.b ? static_cast<const T*>(a.b) + (int64_t)b * a.V : nullptr;
+  T* d = static_cast<T*>(a.dst) + (int64_t)b * a.V * a.dst_cs;
+  const bool vec = (a.dst_cs & 7) == 0;
+  constexpr int U = 4;
+  for (int64_t vb = (int64_t)blockIdx.x * 256 + threadIdx.x; vb < a.V; vb += (int64_t)gridDim.x * 256 * U) {
+    float va[U], vbv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * gridDim.x * 256;
+      va[u] = vbv[u] = 0.f;
+      if (v < a.V) {
+        va[u] = Elem<T>::ld(pa + v) + (a.a_add ? __ldg(a.a_add + v) : 0.f);
+        if (pb) vbv[u] = Elem<T>::ld(pb + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + (int64_t)u * gridDim.x * 256;
+      if (v >= a.V) continue;
+      T* o = d + v * a.dst_cs;
+      if (vec) {
+        float vals[8] = {va[u], vbv[u], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store8(o, vals);
+        const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 8; c < a.dst_cs; c += 8) store8(o + c, zeros);
+      } else {
+        Elem<T>::st(o, va[u]);
+        Elem<T>::st(o + 1, vbv[u]);
+        for (int c = 2; c < a.dst_cs; ++c) Elem<T>::st(o + c, 0.f);
+      }
     }
   }
 }
@@ -200,8 +216,10 @@ extern "C" int coma_roi_paint_bwd(const void* dbuf, const float* is_pos, float* 
 
 extern "C" int coma_pack2_fwd(const coma_pack2_args* a, coma_stream_t stream) {
   COMA_CHECK_ARG(a && a->a && a->dst && a->dst_cs >= 2, "coma_pack2_fwd: bad arguments");   // b may be NULL (zeros)
-  if (a->dtype == COMA_BF16) pack2_kernel<__nv_bfloat16><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
-  else pack2_kernel<float><<<sweep_blocks((int64_t)a->B * a->V), 256, 0, stream>>>(*a);
+  const int64_t want = (a->V + 1023) / 1024, cap = std::max<int64_t>(1, (int64_t)num_sms() * 8 / std::max(1, a->B));
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min(want, cap)), (unsigned)a->B);
+  if (a->dtype == COMA_BF16) pack2_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*a);
+  else pack2_kernel<float><<<grid, 256, 0, stream>>>(*a);
   COMA_CHECK_LAUNCH("pack2");
   return COMA_OK;
 }

@@ -58,38 +58,60 @@ class DevicePrefetcher:
     """Device-side half of the reference's ``DataLoader(pin_memory=True)`` + ``.cuda(non_blocking=True)`` idiom
     (attn_unet_data_parallel.py:795-812): iterates batches (tuples whose tensors live in pinned host memory), issues each
     batch's host->device copies on a dedicated copy stream ``depth - 1`` batches ahead of the consumer, and hands out device
-    tensors that the consumer's current stream may use at once.  Non-tensor items pass through untouched.
+    tensors that the consumer's current stream may use at once.  The device buffers are a fixed ring of ``depth`` slots
+    (allocated on first use, re-allocated if a batch changes shape), so the steady state never touches the allocator; a
+    slot is refilled only after the work the consumer enqueued on it has finished.  Non-tensor items pass through.
     """
 
     def __init__(self, batches, device, depth=2):
         self.batches, self.device, self.depth = batches, torch.device(device), max(1, depth)
         self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None] * self.depth          # per slot: [device tensors..., consumer-done event]
 
-    def _issue(self, batch):
+    def _issue(self, batch, slot):
+        cur = self.slots[slot]
+        same = cur is not None and len(cur[0]) == len(batch) and all(
+            (not torch.is_tensor(t)) or (torch.is_tensor(d) and d.shape == t.shape and d.dtype == t.dtype)
+            for t, d in zip(batch, cur[0]))
+        if not same:
+            bufs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) if torch.is_tensor(t) else None for t in batch]
+            cur = self.slots[slot] = [bufs, None]
+        if cur[1] is not None:
+            self.stream.wait_event(cur[1])          # the consumer's work on this slot's previous batch
         with torch.cuda.stream(self.stream):
-            dev = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            for t, d in zip(batch, cur[0]):
+                if torch.is_tensor(t):
+                    d.copy_(t, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.stream)
-        return dev, ready
-
-    def _hand_out(self, item):
-        dev, ready = item
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ready)
-        for t in dev:
-            if torch.is_tensor(t):
-                t.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
-        return dev
+        return slot, ready, tuple(d if torch.is_tensor(t) else t for t, d in zip(batch, cur[0]))
 
     def __iter__(self):
         from collections import deque
         inflight = deque()
+        n = 0
+
+        def hand_out():
+            slot, ready, dev = inflight.popleft()
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            return slot, dev
+
+        def release(slot):
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            self.slots[slot][1] = done
+
         for batch in self.batches:
-            inflight.append(self._issue(batch))
-            if len(inflight) >= self.depth:
-                yield self._hand_out(inflight.popleft())
+            if len(inflight) >= self.depth:      # every slot holds a batch: hand the oldest to the consumer first
+                slot, dev = hand_out()
+                yield dev
+                release(slot)
+            inflight.append(self._issue(batch, n % self.depth))
+            n += 1
         while inflight:
-            yield self._hand_out(inflight.popleft())
+            slot, dev = hand_out()
+            yield dev
+            release(slot)
 
 
 class HostSink:
