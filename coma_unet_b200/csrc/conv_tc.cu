@@ -792,8 +792,10 @@ __device__ __forceinline__ void ring_epilogue(const HaloParams& p, uint32_t tmem
 }
 
 // EPI epilogue warpgroups (4 warps each) drain alternate output planes: at N <= 32 the epilogue, not the MMA side, was the limit.
-template <int NT, int KC, int KCH, int EPI>
-__global__ void __launch_bounds__(64 + 128 * EPI, 1)
+// CPS = CTAs per SM: with few channels the single MMA-issuing warp's instruction latency (not the tensor pipe, not the epilogue) sets
+// the pace, so two small CTAs per SM (EPI = 1, half the shared memory and TMEM each) give two independent issue streams.
+template <int NT, int KC, int KCH, int EPI, int CPS>
+__global__ void __launch_bounds__(64 + 128 * EPI, CPS)
 conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1368,7 +1370,7 @@ int pick_nt(int cout) {
 }
 
 // ---- halo-reuse (v2) planning ----
-struct HaloPlan { bool ok, s2; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
+struct HaloPlan { bool ok, s2; int ctas; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
 
 HaloPlan plan_halo(const coma_conv_args& a) {
   HaloPlan h{};
@@ -1388,7 +1390,8 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   h.rowb = (uint32_t)(a.Cin / h.KCH) * 2u;
   h.chunk_bytes = ((uint32_t)(a.transposed || h.s2 ? HT_ROWS : HALO_ROWS) * h.rowb + 1023u) & ~1023u;
   h.slab_bytes = h.chunk_bytes * (uint32_t)(h.s2 ? 4 : h.KCH);      // stride 2: four (h,w)-parity sub-slabs per input plane
-  const size_t budget = 222 * 1024;
+  size_t budget = 222 * 1024;
+  h.ctas = 1;
   // v2 / transposed keep three input planes live (+1 in flight); v3 consumes each plane once (+1 in flight)
   const size_t min_slabs = use_v3 ? 2 : 4;
   // N per CTA: all of Cout when the 27 weight tiles fit, otherwise (v3 only) split Cout over grid.y
@@ -1402,6 +1405,17 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   }
   if (h.NT == 0) return h;
   if ((h.KCH > 1 || h.s2) && a.Cout / h.NT > 4) return h;          // too many re-reads of A: the per-tap kernel does better
+  {
+    // two CTAs per SM (stride-1 v3 kernel): everything of one CTA must fit half an SM (shared memory, 256 TMEM columns)
+    static const bool two_off = [] { const char* e = getenv("COMA_DISABLE_HALO_2CTA"); return e && e[0] == '1'; }();
+    const size_t half = (h.NT == 16 ? 72 : 110) * 1024;      // NT = 16: three CTAs per SM
+    const size_t tail2 = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
+    const size_t fixed2 = 1024 + ((27u * h.KCH * h.NT * h.rowb + 1023u) & ~1023u) + tail2;
+    if (!two_off && use_v3 && !h.s2 && h.KCH == 1 && h.NT <= 32 && kRing * h.NT <= 256 && fixed2 + 4 * (size_t)h.slab_bytes <= half) {
+      h.ctas = 2;
+      budget = half;
+    }
+  }
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
   h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
   const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
@@ -1412,7 +1426,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   h.cols_w = (gw + HW_T - 1) / HW_T;
   h.cols_h = (gh + HH_T - 1) / HH_T;
   const int ncols = a.B * h.cols_w * h.cols_h;
-  int segs = (4 * num_sms() + ncols - 1) / ncols;
+  int segs = (4 * num_sms() * h.ctas * (h.ctas == 2 && h.NT == 16 ? 3 : 2) / 2 + ncols - 1) / ncols;
   const int max_segs = (gd + 3) / 4;
   if (segs > max_segs) segs = max_segs;
   if (segs < 1) segs = 1;
@@ -1447,7 +1461,8 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
       cudaFuncSetAttribute(conv_halo_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(convT_halo_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
-    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (KCH == 1 && NT <= 32) cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, 1, 1, (NT == 16 ? 3 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (KCH == 1) cudaFuncSetAttribute(conv_halo_s2_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
@@ -1465,10 +1480,17 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
     p.stat_chunks *= EPI;
     convT_halo_kernel<NT, KC, EPI><<<grid, 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
   }
+  else if (KCH == 1 && NT <= 32 && h.ctas == 2) {
+    constexpr int CPS = NT == 16 ? 3 : 2;
+    int grid2 = CPS * num_sms() / nsplit;
+    if (grid2 < 1) grid2 = 1;
+    if (grid2 > p.total_segs) grid2 = p.total_segs;
+    conv_halo3_kernel<NT, KC, 1, 1, CPS><<<dim3((unsigned)grid2, (unsigned)nsplit), 64 + 128, h.smem, stream>>>(tmA, tmB, p);
+  }
   else if (v3 || KCH > 1) {
     constexpr int EPI = NT <= 32 ? 2 : 1;
     p.stat_chunks *= EPI;
-    conv_halo3_kernel<NT, KC, KCH, EPI><<<dim3((unsigned)grid, (unsigned)nsplit), 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
+    conv_halo3_kernel<NT, KC, KCH, EPI, 1><<<dim3((unsigned)grid, (unsigned)nsplit), 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
   }
   else conv_halo_kernel<NT, KC><<<grid, kTcThreads, h.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_halo");
@@ -1496,7 +1518,7 @@ int conv_tc_stat_chunks(const coma_conv_args& a) {
   const HaloPlan h = plan_halo(a);
   if (h.ok) {
     static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
-    const bool dual = (a.transposed || v3 || h.KCH > 1) && h.NT <= 32;       // two epilogue warpgroups -> two partials per segment
+    const bool dual = (a.transposed || v3 || h.KCH > 1) && h.NT <= 32 && (h.ctas == 1 || a.transposed || h.s2);   // two epilogue warpgroups -> two partials per segment
     return h.cols_w * h.cols_h * h.segs_d * (dual ? 2 : 1);
   }
   int tw, th, td, cl;
