@@ -284,6 +284,8 @@ def kernel_profile(step_fn, n=2):
             if shape[1] > 2.5e8:                      # launches big enough to be bandwidth- rather than latency-bound
                 h[3] = max(h[3], shape[1] / ms / 1e6)
     kernel_profile.hbm = hbm
+    kernel_profile.timeline = [{"call": name + (":tcgen05" if tc else ""), "ms": e0.elapsed_time(e1),
+                                "shape": list(shape) if shape else None} for name, tc, flops, e0, e1, shape in records]
     return fam, layers
 
 
@@ -398,7 +400,8 @@ def run_ours(args):
             json.dump({"hbm_bound_kernels": hbm_roof,
                        "families": {k: {"ms": v[0], "gflop": v[1] / 1e9, "launches": v[2]} for k, v in fam.items()},
                        "conv_layers": [{"kernel": k, "B,Cin,Cout,Do,k,stride,T": s, "ms": ms_, "tflops": fl / ms_ / 1e9}
-                                       for k, s, ms_, fl in layers]}, f, indent=1)
+                                       for k, s, ms_, fl in layers],
+                       "timeline": getattr(kernel_profile, "timeline", [])}, f, indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

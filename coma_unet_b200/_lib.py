@@ -27,7 +27,8 @@ class ConvArgs(C.Structure):
                 ("B", _i32), ("Di", _i32), ("Hi", _i32), ("Wi", _i32), ("Do", _i32), ("Ho", _i32), ("Wo", _i32),
                 ("Cin", _i32), ("Cout", _i32), ("x_cs", _i32), ("x_co", _i32), ("y_cs", _i32), ("y_co", _i32),
                 ("y_cn", _i32), ("ksize", _i32), ("stride", _i32), ("pad", _i32), ("transposed", _i32),
-                ("w_bstride", _i64), ("bias_bstride", _i32), ("act", _i32), ("dtype", _i32), ("impl", _i32)]
+                ("w_bstride", _i64), ("bias_bstride", _i32), ("act", _i32), ("dtype", _i32), ("impl", _i32),
+                ("in_scale", _vp), ("in_shift", _vp), ("in_slope", _vp), ("in_act", _i32), ("reserved0", _i32)]
 
 
 class WgradArgs(C.Structure):
@@ -100,6 +101,7 @@ EXPORTS = {
     "coma_last_error": (C.c_char_p, []),
     "coma_conv3d_stat_chunks": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_tcgen05_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "coma_conv3d_prologue_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "coma_convT3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "coma_conv3d_dgrad": (C.c_int, [C.POINTER(ConvArgs), _vp]),

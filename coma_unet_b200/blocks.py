@@ -154,7 +154,9 @@ class Convolution(nn.Module):
             slope = self._slope_buf
         return code, slope
 
-    def forward(self, x, film=None, out=None, final_relu=False):
+    def forward(self, x, film=None, out=None, final_relu=False, defer=False):
+        """``x`` may be an ``ops.Deferred`` (its producer's norm/activation is applied by this conv's input prologue);
+        ``defer=True`` (no-grad InstanceNorm path only) returns this conv's own output as a Deferred."""
         norm, act = self._parts()
         code, slope = self._slope(act, x.device)
         if final_relu:   # the model's final ReLU folded onto a PReLU head (attn_unet_data_parallel.py:654-656)
@@ -188,6 +190,8 @@ class Convolution(nn.Module):
             raise NotImplementedError("padded outputs with an affine norm")
         eps = norm.eps if norm is not None else 1e-5
         grad = _grad_mode(x, conv.weight, g if torch.is_tensor(g) else None)
+        if grad:
+            x = ops.materialized(x)
 
         # --- eval BatchNorm / no norm, no autograd: everything in the conv epilogue -----------------
         if not grad and mode in (L.NORM_NONE, L.NORM_GIVEN):
@@ -197,7 +201,7 @@ class Convolution(nn.Module):
                 cfg = ops.NormCfg(mode=mode, act=code, eps=eps,
                                   running_mean=getattr(norm, "running_mean", None),
                                   running_var=getattr(norm, "running_var", None))
-                dummy = x.new_empty(B, 1, 1, 1, Cn)
+                dummy = (x.raw if isinstance(x, ops.Deferred) else x).new_empty(B, 1, 1, 1, Cn)
                 scale, shift, _, _, _ = ops.norm_coefficients(dummy, g, h, cfg)
             wp, cout_comp = self._packed(x)
             if scale is not None and cout_comp != Cn:
@@ -208,15 +212,20 @@ class Convolution(nn.Module):
             return y
         # --- general path: conv (+ statistics) then normalise / modulate / activate ------------------
         want_stats = mode in (L.NORM_INSTANCE, L.NORM_BATCH)
+        pro = x if isinstance(x, ops.Deferred) else None
         cfg = ops.ConvCfg(ksize=self.kernel_size, stride=self.strides, transposed=self.is_transposed,
-                          cout_store=store, want_stats=want_stats, bias_grad_zero=want_stats)
-        y, stats = ops.conv3d(x, conv.weight, conv.bias, cfg)
+                          cout_store=store, want_stats=want_stats, bias_grad_zero=want_stats, in_affine=pro)
+        y, stats = ops.conv3d(pro.raw if pro is not None else x, conv.weight, conv.bias, cfg)
         if norm is None and code == L.ACT_NONE:
             if out is not None:
                 ops._copy_channels(y, out)
                 return out
             return y
         ncfg = ops.NormCfg(mode=mode, act=code, eps=eps, stats=stats, out=None if grad else out)
+        if defer and not grad and out is None and mode == L.NORM_INSTANCE and code in (L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY):
+            A, S, _, _, _ = ops.norm_coefficients(y, g, h, ncfg)
+            sl = None if slope is None else slope.detach().float().reshape(-1)[:1].contiguous()
+            return ops.Deferred(y, A, S, code, sl)
         if isinstance(norm, nn.modules.batchnorm._BatchNorm):
             ncfg.running_mean, ncfg.running_var = norm.running_mean, norm.running_var
             ncfg.momentum = 0.1 if norm.momentum is None else norm.momentum

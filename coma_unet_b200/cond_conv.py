@@ -71,13 +71,15 @@ class CondConvolution(Convolution):
             nn.init.zeros_(self.film[2].weight)
             nn.init.zeros_(self.film[2].bias)
 
-    def forward(self, x, covariate=None, out=None):
+    def forward(self, x, covariate=None, out=None, defer=False):
         c = covariate_matrix(covariate, x) if covariate is not None and self.num_covars > 0 else None
         if self.num_experts > 1:
             r = torch.sigmoid(self.routing(c))                                       # [B, E]
             w = torch.einsum("be,eoi->boi", r, self.conv.weight.flatten(2))          # [B, Cout, Cin]
             b = r @ self.conv.bias if self.conv.bias is not None else None           # [B, Cout]
-            y = ops.PerSampleConv1x1Fn.apply(x, w, b)
+            if isinstance(x, ops.Deferred) and torch.is_grad_enabled() and (w.requires_grad or (b is not None and b.requires_grad)):
+                x = x.materialize()
+            y = ops.PerSampleConv1x1Fn.apply(x.raw, w, b, x) if isinstance(x, ops.Deferred) else ops.PerSampleConv1x1Fn.apply(x, w, b)
             if out is not None:
                 ops._copy_channels(y, out)
                 return out
@@ -85,7 +87,7 @@ class CondConvolution(Convolution):
         film = None
         if self.film is not None and c is not None:
             film = self.film(c).chunk(2, dim=-1)
-        return super().forward(x, film=film, out=out)
+        return super().forward(x, film=film, out=out, defer=defer)
 
 
 class CondConvBlock(nn.Module):

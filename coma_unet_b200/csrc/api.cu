@@ -24,6 +24,8 @@ int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool conv_tc_supported(const coma_conv_args& a);
 int conv_tc_stat_chunks(const coma_conv_args& a);
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream);
+bool conv_tc_prologue_supported(const coma_conv_args& a);
+bool conv_simt_prologue_fused(const coma_conv_args& a);
 
 static int check_conv(const coma_conv_args* a, const char* who) {
   COMA_CHECK_ARG(a && a->x && a->w && a->y, "%s: null tensor", who);
@@ -35,6 +37,10 @@ static int check_conv(const coma_conv_args* a, const char* who) {
   COMA_CHECK_ARG((a->scale == nullptr) == (a->shift == nullptr), "%s: scale and shift go together", who);
   COMA_CHECK_ARG(a->y_cn > 0 && a->y_cn <= a->Cout && a->y_co + a->y_cn <= a->y_cs, "%s: bad output channel view", who);
   COMA_CHECK_ARG(a->x_co + a->Cin <= a->x_cs, "%s: bad input channel view", who);
+  COMA_CHECK_ARG((a->in_scale == nullptr) == (a->in_shift == nullptr), "%s: in_scale and in_shift go together", who);
+  COMA_CHECK_ARG(!a->in_scale || a->in_act == COMA_ACT_NONE || a->in_act == COMA_ACT_RELU || (a->in_act == COMA_ACT_LEAKY && a->in_slope),
+                 "%s: the input prologue takes act none / relu / leaky(+slope)", who);
+  COMA_CHECK_ARG(!a->in_scale || !a->transposed, "%s: no input prologue on transposed convolutions", who);
   if (!a->transposed) {
     COMA_CHECK_ARG(a->Do == (a->Di + 2 * a->pad - a->ksize) / a->stride + 1 && a->Ho == (a->Hi + 2 * a->pad - a->ksize) / a->stride + 1 &&
                        a->Wo == (a->Wi + 2 * a->pad - a->ksize) / a->stride + 1, "%s: output extents do not match the conv geometry", who);
@@ -81,6 +87,11 @@ extern "C" int coma_conv3d_stat_chunks(const coma_conv_args* a) {
   return impl == COMA_IMPL_TCGEN05 ? conv_tc_stat_chunks(*a) : conv_simt_stat_chunks(*a);
 }
 extern "C" int coma_conv3d_tcgen05_supported(const coma_conv_args* a) { return a && conv_tc_supported(*a) ? 1 : 0; }
+extern "C" int coma_conv3d_prologue_supported(const coma_conv_args* a) {
+  if (!a || a->transposed) return 0;
+  const int impl = pick_impl(*a);
+  return (impl == COMA_IMPL_TCGEN05 ? conv_tc_prologue_supported(*a) : conv_simt_prologue_fused(*a)) ? 1 : 0;
+}
 
 extern "C" int coma_conv3d_fprop(const coma_conv_args* a, coma_stream_t stream) {
   COMA_CHECK_ARG(a && !a->transposed, "coma_conv3d_fprop: use coma_convT3d_fprop for transposed convolutions");

@@ -29,6 +29,9 @@ __global__ void __launch_bounds__(kSimtThreads) conv_simt_kernel(coma_conv_args 
     const int ow = (int)(v % a.Wo), oh = (int)((v / a.Wo) % a.Ho), od = (int)(v / ((int64_t)a.Wo * a.Ho));
     const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.Di * a.Hi * a.Wi * a.x_cs + a.x_co;
     const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride;
+    const float* isc = a.in_scale ? a.in_scale + (int64_t)b * a.Cin : nullptr;       // input prologue (reference implementation)
+    const float* ish = a.in_scale ? a.in_shift + (int64_t)b * a.Cin : nullptr;
+    const float ineg = a.in_act == COMA_ACT_NONE ? 1.f : (a.in_act == COMA_ACT_RELU ? 0.f : (a.in_slope ? __ldg(a.in_slope) : 0.f));
     for (int kd = 0; kd < K; ++kd) {
       int id;
       if (!a.transposed) {
@@ -66,6 +69,13 @@ __global__ void __launch_bounds__(kSimtThreads) conv_simt_kernel(coma_conv_args 
             for (int ci = 0; ci < a.Cin; ci += 8) {
               float xv[8];
               load8(xp + ci, xv);
+              if (isc) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float u = fmaf(__ldg(isc + ci + e), xv[e], __ldg(ish + ci + e));
+                  xv[e] = fmaf(ineg, fminf(u, 0.f), fmaxf(u, 0.f));
+                }
+              }
 #pragma unroll
               for (int j = 0; j < COT; ++j) {
                 if (co0 + j < a.Cout) {
@@ -78,7 +88,11 @@ __global__ void __launch_bounds__(kSimtThreads) conv_simt_kernel(coma_conv_args 
             }
           } else {
             for (int ci = 0; ci < a.Cin; ++ci) {
-              const float xs = Elem<T>::ld(xp + ci);
+              float xs = Elem<T>::ld(xp + ci);
+              if (isc) {
+                const float u = fmaf(__ldg(isc + ci), xs, __ldg(ish + ci));
+                xs = fmaf(ineg, fminf(u, 0.f), fmaxf(u, 0.f));
+              }
 #pragma unroll
               for (int j = 0; j < COT; ++j)
                 if (co0 + j < a.Cout) acc[j] = fmaf(xs, Elem<T>::ld(wp + (int64_t)j * a.Cin + ci), acc[j]);
@@ -170,9 +184,15 @@ __global__ void __launch_bounds__(kPwThreads) conv_pw1_kernel(coma_conv_args a, 
   const T* xb = static_cast<const T*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co + part * CPL;
   const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride + part * CPL;
   T* yb = static_cast<T*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co;
-  float w[CPL];
+  float w[CPL], isc[CPL], ish[CPL];
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) w[c] = Elem<T>::ld(wb + c);
+  for (int c = 0; c < CPL; ++c) {
+    w[c] = Elem<T>::ld(wb + c);
+    isc[c] = a.in_scale ? __ldg(a.in_scale + (int64_t)b * a.Cin + part * CPL + c) : 1.f;
+    ish[c] = a.in_scale ? __ldg(a.in_shift + (int64_t)b * a.Cin + part * CPL + c) : 0.f;
+  }
+  const bool pro = a.in_scale != nullptr;
+  const float ineg = a.in_act == COMA_ACT_NONE ? 1.f : (a.in_act == COMA_ACT_RELU ? 0.f : (a.in_slope ? __ldg(a.in_slope) : 0.f));
   const float bias = a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride) : 0.f;
   const float slope = a.slope ? __ldg(a.slope) : 0.f;
   const float sc = a.scale ? __ldg(a.scale + (int64_t)b * a.Cout) : 1.f, sh = a.scale ? __ldg(a.shift + (int64_t)b * a.Cout) : 0.f;
@@ -201,8 +221,16 @@ __global__ void __launch_bounds__(kPwThreads) conv_pw1_kernel(coma_conv_args a, 
     for (int u = 0; u < U; ++u) {
       const int64_t v = vb + (int64_t)u * VPB;
       float acc = 0.f;
+      if (pro) {        // producer's norm + FiLM + activation applied on load
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) acc = fmaf(xv[u][c], w[c], acc);
+        for (int c = 0; c < CPL; ++c) {
+          const float t = fmaf(isc[c], xv[u][c], ish[c]);
+          acc = fmaf(fmaf(ineg, fminf(t, 0.f), fmaxf(t, 0.f)), w[c], acc);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc = fmaf(xv[u][c], w[c], acc);
+      }
 #pragma unroll
       for (int o = 1; o < LPV; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (v < v1 && part == 0) {
@@ -254,6 +282,8 @@ static int launch_pw1_t(const coma_conv_args& a, cudaStream_t stream) {
   COMA_CHECK_LAUNCH("conv_pw1");
   return COMA_OK;
 }
+
+bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a); }
 
 int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : simt_chunks(a); }
 

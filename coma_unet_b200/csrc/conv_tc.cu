@@ -456,6 +456,9 @@ struct HaloParams {
   float* stats;
   int act, stat_chunks;
   uint32_t tmem_cols;
+  const float* in_scale; const float* in_shift;   // input prologue (v3 stride-1 kernel): x' = max(u,0) + in_neg*min(u,0), u = in_scale*x + in_shift
+  const float* in_slope;
+  int in_act;
 };
 
 struct SegCoord { int b, d0, nd, h0, w0, chunk; };
@@ -803,16 +806,20 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);
   uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
   uint64_t* sempty = sfull + kMaxSlabs;
-  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* sready = sempty + kMaxSlabs;                                 // prologue: slab transformed in place, MMA may read it
+  uint64_t* wfull = sready + kMaxSlabs;
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + kRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kRing);
   float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+  float* xcoef = sstat + 22 * NT;                                         // [2][64]: prologue scale, shift of the current sample
+  constexpr int XW = 1;                                                   // transform warps (a second one cost more in registers than it gained)
+  const bool pro = KCH == 1 && CPS > 1 && KC <= 32 && p.in_scale != nullptr;     // only the small-channel (multi-CTA) variants carry the prologue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * NT;          // this CTA's slice of the output channels (Cout split when the weights do not fit)
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); mbar_init(&sready[s], XW); }
     mbar_init(wfull, 1);
     for (int a = 0; a < kRing; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -828,6 +835,90 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+// ---- input prologue (transform warps: warp 0 and, in the multi-CTA variants, one helper warp after the epilogue warps)
+auto prologue_walk = [&](const int widx) {
+    // Each transform warp walks the plane sequence; warp 0 also runs LAG planes ahead issuing the TMA loads (lane 0).  The warps
+    // rewrite an arrived slab in place (x' = act(scale*x + shift) on in-bounds voxels; the zero-filled halo outside the
+    // volume IS the padding of the activated tensor and stays zero) and hand it to the MMA warp through sready.
+    constexpr uint32_t ROWB = KC * 2u, CPR = ROWB / 16u, SWM = CPR - 1u;     // chunks (16 B) per row; swizzle mask on the chunk index
+    struct Cur { int t, pi; SegCoord sc; uint32_t slot, ph; bool valid; };
+    auto cur_init = [&](Cur& c) { c.t = blockIdx.x; c.pi = 0; c.slot = 0; c.ph = 0; c.valid = c.t < p.total_segs; if (c.valid) c.sc = decode_seg(p, c.t); };
+    auto cur_next = [&](Cur& c) {
+      if (++c.slot == (uint32_t)p.nslab) { c.slot = 0; c.ph ^= 1u; }
+      if (++c.pi == c.sc.nd + 2) { c.pi = 0; c.t += gridDim.x; c.valid = c.t < p.total_segs; if (c.valid) c.sc = decode_seg(p, c.t); }
+    };
+    const float in_neg = p.in_act == COMA_ACT_NONE ? 1.f : (p.in_act == COMA_ACT_RELU ? 0.f : __ldg(p.in_slope));
+    const int lag = min(p.nslab - 1, 4);
+    Cur is, xf;
+    cur_init(is);
+    cur_init(xf);
+    int ahead = 0, staged_b = -1;
+    uint32_t av2[4] = {0, 0, 0, 0}, bv2[4] = {0, 0, 0, 0};      // packed bf16x2 scale / shift of this lane's channel group
+    const uint32_t neg2 = pack_bf16x2(in_neg, in_neg);
+    while (xf.valid) {
+      while (is.valid && ahead < lag) {
+        if (widx == 0 && lane == 0) {
+          mbar_wait(&sempty[is.slot], is.ph ^ 1u);
+          mbar_expect_tx(&sfull[is.slot], p.slab_tx);
+          tma_load_5d(slabs + (size_t)is.slot * p.slab_bytes, &tmA, &sfull[is.slot], 0, is.sc.w0 - 1, is.sc.h0 - 1, is.sc.d0 - 1 + is.pi, is.sc.b);
+        }
+        cur_next(is);
+        ++ahead;
+      }
+      __syncwarp();
+      // lane L always meets the same logical 8-channel group: chunk c = L + 32 k has c % CPR = L % CPR and swizzle term
+      // (c >> 3) % CPR = (L >> 3) % CPR for CPR <= 4, so its 8 scales / shifts live in registers per sample
+      if (xf.sc.b != staged_b) {
+        staged_b = xf.sc.b;
+        const uint32_t jl = ((uint32_t)lane & SWM) ^ (((uint32_t)lane >> 3) & SWM);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* sc2 = p.in_scale + (int64_t)staged_b * p.Cin + jl * 8 + 2 * j;
+          const float* sh2 = p.in_shift + (int64_t)staged_b * p.Cin + jl * 8 + 2 * j;
+          av2[j] = pack_bf16x2(__ldg(sc2), __ldg(sc2 + 1));
+          bv2[j] = pack_bf16x2(__ldg(sh2), __ldg(sh2 + 1));
+        }
+      }
+      mbar_wait(&sfull[xf.slot], xf.ph);
+      const int d = xf.sc.d0 - 1 + xf.pi;
+      if (d >= 0 && d < p.D) {
+        uint8_t* slab = slabs + (size_t)xf.slot * p.slab_bytes;
+        constexpr uint32_t NCH = (uint32_t)HALO_ROWS * CPR;
+        for (uint32_t c0 = lane + 32u * widx; c0 < NCH; c0 += 128u * XW) {       // four chunks per lane in flight
+          uint4 q[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t c = c0 + 32u * XW * u, r = c / CPR;
+            const int gh = xf.sc.h0 - 1 + (int)(r / HALO_W), gw = xf.sc.w0 - 1 + (int)(r % HALO_W);
+            ok[u] = c < NCH && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+            if (ok[u]) q[u] = *reinterpret_cast<const uint4*>(slab + c * 16u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            uint32_t wd[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // packed bf16x2: u = fma(scale, x, shift) rounded once, then max(u,0) + neg * min(u,0)
+              uint32_t uu, lo, hi;
+              asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(uu) : "r"(av2[j]), "r"(wd[j]), "r"(bv2[j]));
+              asm("min.bf16x2 %0, %1, %2;" : "=r"(lo) : "r"(uu), "r"(0u));
+              asm("max.bf16x2 %0, %1, %2;" : "=r"(hi) : "r"(uu), "r"(0u));
+              asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(wd[j]) : "r"(neg2), "r"(lo), "r"(hi));
+            }
+            *reinterpret_cast<uint4*>(slab + (c0 + 32u * XW * u) * 16u) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sready[xf.slot]);
+      cur_next(xf);
+      --ahead;
+    }
+  };
+
   if (warp == 0) {
     // ================================ TMA producer =================================
     if (lane == 0) {
@@ -836,19 +927,22 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kc = 0; kc < KCH; ++kc)
           for (int kd = 0; kd < 3; ++kd)
             tma_load_2d(wreg + (size_t)((t9 * KCH + kc) * 3 + kd) * p.w_tile_bytes, &tmB, wfull, kc * KC, (kd * 9 + t9) * p.Cout + n0);
-      uint32_t slot = 0, ph = 0;
-      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
-        const SegCoord sc = decode_seg(p, t);
-        for (int pi = 0; pi < sc.nd + 2; ++pi) {
-          mbar_wait(&sempty[slot], ph ^ 1u);
-          mbar_expect_tx(&sfull[slot], p.slab_tx);
-          for (int kc = 0; kc < KCH; ++kc)
-            tma_load_5d(slabs + (size_t)slot * p.slab_bytes + (size_t)kc * p.chunk_bytes, &tmA, &sfull[slot], kc * KC, sc.w0 - 1, sc.h0 - 1,
-                        sc.d0 - 1 + pi, sc.b);
-          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+      if (!pro) {
+        uint32_t slot = 0, ph = 0;
+        for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+          const SegCoord sc = decode_seg(p, t);
+          for (int pi = 0; pi < sc.nd + 2; ++pi) {
+            mbar_wait(&sempty[slot], ph ^ 1u);
+            mbar_expect_tx(&sfull[slot], p.slab_tx);
+            for (int kc = 0; kc < KCH; ++kc)
+              tma_load_5d(slabs + (size_t)slot * p.slab_bytes + (size_t)kc * p.chunk_bytes, &tmA, &sfull[slot], kc * KC, sc.w0 - 1, sc.h0 - 1,
+                          sc.d0 - 1 + pi, sc.b);
+            if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+          }
         }
       }
     }
+    if (pro) prologue_walk(0);
   } else if (warp == 1) {
     // ================================ MMA issuer (warp-uniform loop, one elected lane issues) ============
     const bool leader = elect_one();
@@ -869,7 +963,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
       const SegCoord sc = decode_seg(p, t);
       for (int pi = 0; pi < sc.nd + 2; ++pi) {
-        mbar_wait(&sfull[sslot], sph);
+        mbar_wait(pro ? &sready[sslot] : &sfull[sslot], sph);
         const int kd_lo = max(0, pi - sc.nd + 1), kd_hi = min(2, pi);
         if (kd_lo == 0) {       // block s starts a new output plane: its previous tenant must have been drained
           mbar_wait(&tempty[s], ((pbits >> s) & 1u) ^ 1u);
@@ -943,7 +1037,7 @@ conv_halo3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         s = (s + kRing - 1) & (kRing - 1);
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * EPI) {
     ring_epilogue<NT, EPI, 2>(p, tmem_base, tfull, tempty, sstat, n0, warp, lane);
   }
 
@@ -1370,6 +1464,10 @@ int pick_nt(int cout) {
 }
 
 // ---- halo-reuse (v2) planning ----
+// barriers (sfull, sempty, sready per slab; wfull; tfull, tempty per ring block), the TMEM slot, two epilogue groups of
+// [4 warps][NT][2] stat partials + cA, cS, cB, and the prologue coefficients (scale, shift for up to 64 input channels)
+static size_t halo_tail_bytes(int nt) { return (3 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * nt * sizeof(float) + 64 + 2 * 64 * sizeof(float); }
+
 struct HaloPlan { bool ok, s2; int ctas; int cols_w, cols_h, segs_d, DS, nslab, NT, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_tile_bytes, w_bytes; size_t smem; };
 
 HaloPlan plan_halo(const coma_conv_args& a) {
@@ -1399,7 +1497,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   for (int nt : {64, 32, 16}) {
     if (a.Cout % nt != 0) continue;
     if (nt != a.Cout && !use_v3) continue;
-    const size_t tail_nt = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * nt * sizeof(float) + 64;
+    const size_t tail_nt = halo_tail_bytes(nt);
     const size_t fixed_nt = 1024 + ((27u * h.KCH * nt * h.rowb + 1023u) & ~1023u) + tail_nt;
     if (fixed_nt + min_slabs * (size_t)h.slab_bytes <= budget) { h.NT = nt; break; }
   }
@@ -1409,7 +1507,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
     // two CTAs per SM (stride-1 v3 kernel): everything of one CTA must fit half an SM (shared memory, 256 TMEM columns)
     static const bool two_off = [] { const char* e = getenv("COMA_DISABLE_HALO_2CTA"); return e && e[0] == '1'; }();
     const size_t half = (h.NT == 16 ? 72 : 110) * 1024;      // NT = 16: three CTAs per SM
-    const size_t tail2 = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
+    const size_t tail2 = halo_tail_bytes(h.NT);
     const size_t fixed2 = 1024 + ((27u * h.KCH * h.NT * h.rowb + 1023u) & ~1023u) + tail2;
     if (!two_off && use_v3 && !h.s2 && h.KCH == 1 && h.NT <= 32 && kRing * h.NT <= 256 && fixed2 + 4 * (size_t)h.slab_bytes <= half) {
       h.ctas = 2;
@@ -1418,7 +1516,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   }
   h.w_tile_bytes = (uint32_t)h.NT * h.rowb;
   h.w_bytes = 27u * (uint32_t)h.KCH * h.w_tile_bytes;
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kRing) * 8 + 16 + (size_t)22 * h.NT * sizeof(float) + 64;
+  const size_t tail = halo_tail_bytes(h.NT);
   const size_t fixed = 1024 + ((h.w_bytes + 1023u) & ~1023u) + tail;
   int nslab = (int)((budget - fixed) / h.slab_bytes);
   h.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
@@ -1450,6 +1548,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
   p.stat_chunks = h.cols_w * h.cols_h * h.segs_d;
+  p.in_scale = a.in_scale; p.in_shift = a.in_shift; p.in_slope = a.in_slope; p.in_act = a.in_act;
   static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
   uint32_t cols = 32;
   const uint32_t need = tr ? ((8u * NT * 2u <= 512u) ? 16u * NT : 8u * NT) : (v3 ? (uint32_t)kRing * NT : 2u * NT);
@@ -1462,7 +1561,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
       cudaFuncSetAttribute(convT_halo_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (KCH == 1 && NT <= 32) cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, 1, 1, (NT == 16 ? 3 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if constexpr (KCH == 1 && NT <= 32) cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, 1, 1, (NT == 16 ? 3 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (KCH == 1) cudaFuncSetAttribute(conv_halo_s2_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
@@ -1481,11 +1580,13 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
     convT_halo_kernel<NT, KC, EPI><<<grid, 64 + 128 * EPI, h.smem, stream>>>(tmA, tmB, p);
   }
   else if (KCH == 1 && NT <= 32 && h.ctas == 2) {
+   if constexpr (KCH == 1 && NT <= 32) {
     constexpr int CPS = NT == 16 ? 3 : 2;
     int grid2 = CPS * num_sms() / nsplit;
     if (grid2 < 1) grid2 = 1;
     if (grid2 > p.total_segs) grid2 = p.total_segs;
     conv_halo3_kernel<NT, KC, 1, 1, CPS><<<dim3((unsigned)grid2, (unsigned)nsplit), 64 + 128, h.smem, stream>>>(tmA, tmB, p);
+   }
   }
   else if (v3 || KCH > 1) {
     constexpr int EPI = NT <= 32 ? 2 : 1;
@@ -1499,7 +1600,19 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 }  // namespace
 
+// the input prologue lives in the stride-1 plane-ring kernel (one K chunk): everything else declines it
+bool conv_tc_prologue_supported(const coma_conv_args& a) {
+  if (!a.in_scale) return true;
+  if (a.transposed || a.stride != 1 || a.ksize != 3 || a.dtype != COMA_BF16) return false;
+  static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
+  coma_conv_args b = a;
+  b.in_scale = b.in_shift = nullptr;
+  const HaloPlan h = plan_halo(b);
+  return v3 && h.ok && !h.s2 && h.KCH == 1 && h.ctas == 2 && a.Cin <= 32;
+}
+
 bool conv_tc_supported(const coma_conv_args& a) {
+  if (a.in_scale && !conv_tc_prologue_supported(a)) return false;
   if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
   if (a.act == COMA_ACT_SIGMOID) return false;   // epilogue: relu-family activations only
   if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;

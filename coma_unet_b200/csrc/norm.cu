@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(coma_norm_finalize_a
 // ---- apply: y = act(A*x + S) ---------------------------------------------------------------------
 // SIMPLE: act in {none, relu, leaky/prelu} evaluated as max(u,0) + neg * min(u,0) (no per-element dispatch on the act code)
 template <typename T, int U, bool SIMPLE, bool HASR>
-__global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_act_args a, int chunks) {
+__global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_act_args a, int chunks, int creal) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int CV = a.C >> 3, lanes = kThreads / CV;
   const int cvec = threadIdx.x % CV, vlane = threadIdx.x / CV;
@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(kThreads) affine_act_vec_kernel(coma_affine_ac
   float A8[8], S8[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    A8[e] = a.A[(int64_t)b * a.C + cvec * 8 + e];
-    S8[e] = a.S[(int64_t)b * a.C + cvec * 8 + e];
+    // creal > 0: a dense tensor with fewer than 8 channels viewed as 8-wide vectors (creal divides 8)
+    const int64_t ci = creal > 0 ? (int64_t)b * creal + (e % creal) : (int64_t)b * a.C + cvec * 8 + e;
+    A8[e] = a.A[ci];
+    S8[e] = a.S[ci];
   }
   const float slope = a.slope ? __ldg(a.slope) : 0.f;
   const float neg = a.act == COMA_ACT_NONE ? 1.f : (a.act == COMA_ACT_RELU ? 0.f : slope);
@@ -452,20 +454,33 @@ extern "C" int coma_norm_stats_finalize(const coma_norm_finalize_args* a, coma_s
 
 extern "C" int coma_norm_film_act_fwd(const coma_affine_act_args* a, coma_stream_t stream) {
   COMA_CHECK_ARG(a && a->x && a->y && a->A && a->S && a->B > 0 && a->C > 0 && a->V > 0, "coma_norm_film_act_fwd: bad arguments");
-  const bool vec = vec_ok(a->x, a->C, a->x_cs, a->x_co, a->dtype) && vec_ok(a->y, a->C, a->y_cs, a->y_co, a->dtype) &&
-                   (!a->r || vec_ok(a->r, a->C, a->r_cs, 0, a->dtype));
+  bool vec = vec_ok(a->x, a->C, a->x_cs, a->x_co, a->dtype) && vec_ok(a->y, a->C, a->y_cs, a->y_co, a->dtype) &&
+             (!a->r || vec_ok(a->r, a->C, a->r_cs, 0, a->dtype));
+  coma_affine_act_args v = *a;
+  int creal = 0;
+  if (!vec && a->C < 8 && 8 % a->C == 0 && a->x_cs == a->C && a->y_cs == a->C && a->x_co == 0 && a->y_co == 0 &&
+      (!a->r || a->r_cs == a->C) && (a->V * a->C) % 8 == 0) {
+    // dense tensor with 1 / 2 / 4 channels (the modulator heads): sweep it as 8-wide vectors, coefficients repeat every C
+    v.C = 8; v.V = a->V * a->C / 8; v.x_cs = v.y_cs = 8; v.r_cs = a->r ? 8 : 0;
+    if (vec_ok(v.x, 8, 8, 0, v.dtype) && vec_ok(v.y, 8, 8, 0, v.dtype) && (!v.r || vec_ok(v.r, 8, 8, 0, v.dtype))) {
+      vec = true;
+      creal = a->C;
+    } else {
+      v = *a;
+    }
+  }
   if (vec) {
     static const int env_chunks = [] { const char* e = getenv("COMA_AFFINE_CHUNKS"); return e ? atoi(e) : 0; }();
-    int chunks = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
+    int chunks = (int)std::min<int64_t>(std::max<int64_t>((v.V * (v.C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
     if (env_chunks > 0) chunks = env_chunks;
     dim3 grid((unsigned)chunks, (unsigned)a->B);
     const bool simple = a->act == COMA_ACT_NONE || a->act == COMA_ACT_RELU || a->act == COMA_ACT_LEAKY;
 #define COMA_AFFINE_LAUNCH(T, U)                                                                                     \
     do {                                                                                                              \
-      if (simple && !a->r) affine_act_vec_kernel<T, U, true, false><<<grid, kThreads, 0, stream>>>(*a, chunks);       \
-      else if (simple) affine_act_vec_kernel<T, U, true, true><<<grid, kThreads, 0, stream>>>(*a, chunks);            \
-      else if (!a->r) affine_act_vec_kernel<T, U, false, false><<<grid, kThreads, 0, stream>>>(*a, chunks);           \
-      else affine_act_vec_kernel<T, U, false, true><<<grid, kThreads, 0, stream>>>(*a, chunks);                       \
+      if (simple && !v.r) affine_act_vec_kernel<T, U, true, false><<<grid, kThreads, 0, stream>>>(v, chunks, creal);   \
+      else if (simple) affine_act_vec_kernel<T, U, true, true><<<grid, kThreads, 0, stream>>>(v, chunks, creal);        \
+      else if (!v.r) affine_act_vec_kernel<T, U, false, false><<<grid, kThreads, 0, stream>>>(v, chunks, creal);       \
+      else affine_act_vec_kernel<T, U, false, true><<<grid, kThreads, 0, stream>>>(v, chunks, creal);                   \
     } while (0)
     if (a->dtype == COMA_BF16) COMA_AFFINE_LAUNCH(__nv_bfloat16, 2);
     else COMA_AFFINE_LAUNCH(float, 1);

@@ -77,8 +77,9 @@ class AttentionLayer(blocks.AttentionLayer):
         self.save_attn = status
         self.attention.save_attn = status
 
-    def forward(self, x, covariate=None):
-        """-> (decoder output, encoder tensors from this level down, decoder tensors from this level down)."""
+    def forward(self, x, covariate=None, defer_out=False):
+        """-> (decoder output, encoder tensors from this level down, decoder tensors from this level down).
+        ``defer_out`` (no-grad only): the merge conv's norm + activation is left to the consumer (ops.Deferred)."""
         cov5 = covariate[:, :, :5] if covariate is not None else None
         if isinstance(self.submodule, nn.Sequential):
             block, deeper = self.submodule[0], self.submodule[1]
@@ -101,7 +102,7 @@ class AttentionLayer(blocks.AttentionLayer):
             save_attention_coeffs(self.save_attn, coeff)
         if grad:
             cat = ops.concat2(att, fromlower)
-        att_m = self.merge(cat)
+        att_m = self.merge(cat, defer=defer_out and not grad)
         return att_m, [x] + encs, [att_m] + decs
 
 
@@ -164,14 +165,15 @@ class ObservableAttentionUnet(nn.Module):
         self.compute_dtype = dtype
         return self
 
-    def _backbone(self, xv, covariate):
-        """NDHWC in, NDHWC out: (x[B,D,H,W,out], encoder tensors, decoder tensors)."""
+    def _backbone(self, xv, covariate, defer=False):
+        """NDHWC in, NDHWC out: (x[B,D,H,W,out], encoder tensors, decoder tensors).  ``defer``: the last decoder tensor is only
+        consumed by reduce_channels, whose input prologue applies its InstanceNorm/FiLM/PReLU (decs[0] is then an ops.Deferred)."""
         head, encdec, reduce_channels = self.model
         if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1:
             # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the tensor-core path
             xv = ops.Pack2Fn.apply(xv, None, None, 16)
         h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
-        d, encs, decs = encdec(h, covariate)
+        d, encs, decs = encdec(h, covariate, defer_out=defer)
         return reduce_channels(d, covariate=covariate), encs, decs
 
     def forward(self, x, covariate=None):
@@ -200,6 +202,7 @@ class StackedFusionConvLayers(nn.Module):
                  nonlin=nn.LeakyReLU, nonlin_kwargs=None):
         super().__init__()
         self.input_channels, self.output_channels = input_feature_channels, output_feature_channels
+        self.fuse_prologue = False
         act = (nonlin, nonlin_kwargs or {"negative_slope": 1e-2, "inplace": True})
         widths = [input_feature_channels] + [bottleneck_feature_channel] * (num_convs - 1) + [output_feature_channels]
         # intermediate tensors keep 16 channels (zero padded) so every conv is tcgen05-shaped
@@ -208,7 +211,14 @@ class StackedFusionConvLayers(nn.Module):
             for i in range(num_convs)])
 
     def forward(self, x):
-        return self.blocks(x)
+        # ``fuse_prologue``: without autograd each conv hands its InstanceNorm + LeakyReLU to the next conv's input prologue
+        # (in-shared-memory transform of the halo slabs).  Measured break-even at 16 channels (one transform warp per CTA
+        # vs. a 84%-of-peak norm sweep), so it is off by default; the reduce_channels prologue (model._backbone) is on.
+        defer = self.fuse_prologue and not torch.is_grad_enabled()
+        last = len(self.blocks) - 1
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, defer=defer and i < last)
+        return x
 
 
 class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
@@ -303,7 +313,7 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
             covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
         with blocks.bn_updates(2):   # the reference's duplicated backbone pass (:664,666) in closed form
-            out, encoder_extractions, _ = self._backbone(xv, covariate)
+            out, encoder_extractions, _ = self._backbone(xv, covariate, defer=not torch.is_grad_enabled())
         out = self.forward_modulator_with_uq(x, out, covariate, roi_pred_dicts, sample_roi_mask)
         pred = ops.vol_to_ncdhw(out).float()
         if not self.training and not self.embeddings_out:

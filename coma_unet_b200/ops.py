@@ -125,10 +125,35 @@ def _run_conv(a: L.ConvArgs, kind: str):
     L.call(kind, C.byref(a), L.stream())
 
 
+@dataclass
+class Deferred:
+    """A conv output whose norm + FiLM + activation has not been applied yet: ``act(A[b,c] * raw + S[b,c])``.
+    A consumer conv that supports the input prologue (include/coma_b200.h, coma_conv_args.in_scale) applies it on load;
+    anything else calls ``materialize()`` (one coma_norm_film_act_fwd sweep, what the producer would have run)."""
+    raw: torch.Tensor
+    A: torch.Tensor
+    S: torch.Tensor
+    act: int
+    slope: Optional[torch.Tensor]
+
+    shape = property(lambda self: self.raw.shape)
+    dtype = property(lambda self: self.raw.dtype)
+    device = property(lambda self: self.raw.device)
+    requires_grad = False
+
+    def materialize(self, out=None):
+        return affine_act(self.raw, self.A, self.S, self.slope, self.act, out=out)
+
+
+def materialized(x):
+    return x.materialize() if isinstance(x, Deferred) else x
+
+
 def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None, scale=None, shift=None, slope=None,
              act=L.ACT_NONE, want_stats=False, out=None, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, kind=None):
-    """One conv kernel launch on packed weights.  Returns (y, stats_partial or None)."""
-    x = as_vol(x)
+    """One conv kernel launch on packed weights.  Returns (y, stats_partial or None).  ``x`` may be a Deferred."""
+    pro = x if isinstance(x, Deferred) else None
+    x = as_vol(pro.raw if pro is not None else x)
     B, Di, Hi, Wi, Cin = x.shape
     per = wp.shape[-3:] if w_bstride else wp.shape
     taps, cout_comp, cin_w = per
@@ -144,6 +169,13 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
     a = _conv_args(x, wp, None if bias is None else bias.float().contiguous(), y, ksize=ksize, stride=stride,
                    transposed=transposed, cout_comp=cout_comp, scale=scale, shift=shift, slope=slope, act=act, impl=impl,
                    w_bstride=w_bstride, bias_bstride=bias_bstride)
+    if pro is not None:
+        a.in_scale, a.in_shift, a.in_slope, a.in_act = L.ptr(pro.A), L.ptr(pro.S), L.ptr(pro.slope), pro.act
+        if pro.act not in (L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY) or not L.lib().coma_conv3d_prologue_supported(C.byref(a)):
+            x = pro.materialize()                      # no fused prologue for this shape: apply it the ordinary way
+            a.x, a.x_cs = L.ptr(x), vol_cs(x)
+            a.in_scale = a.in_shift = a.in_slope = None
+            a.in_act = 0
     stats = None
     if want_stats:
         chunks = L.lib().coma_conv3d_stat_chunks(C.byref(a))
@@ -188,6 +220,7 @@ class ConvCfg:
     want_stats: bool = False
     bias_grad_zero: bool = False       # a mean-subtracting norm follows: d bias == 0 exactly
     impl: int = L.IMPL_AUTO
+    in_affine: Optional["Deferred"] = None   # input prologue (no-grad paths)
 
 
 class ConvFn(torch.autograd.Function):
@@ -195,6 +228,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, cfg: ConvCfg):
+        pro = cfg.in_affine            # Deferred producer (no-grad only): x is its raw tensor
         x = as_vol(x)
         cin_buf = x.shape[-1]
         cout_w = weight.shape[1] if cfg.transposed else weight.shape[0]
@@ -202,7 +236,7 @@ class ConvFn(torch.autograd.Function):
         use_tc_pad = x.dtype == torch.bfloat16 and cin_buf % 16 == 0 and cfg.impl != L.IMPL_SIMT
         cout_comp = max(_round_up(cout_w, 16) if use_tc_pad else cout_w, cout_store)
         wp = pack_weight(weight, cfg.transposed, cin_buf, cout_comp, x.dtype)
-        y, stats = conv_raw(x, wp, bias, ksize=cfg.ksize, stride=cfg.stride, transposed=cfg.transposed,
+        y, stats = conv_raw(pro if pro is not None else x, wp, bias, ksize=cfg.ksize, stride=cfg.stride, transposed=cfg.transposed,
                             cout_store=cout_store, want_stats=cfg.want_stats, impl=cfg.impl)
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cout_comp, ctx.has_bias = cfg, cout_comp, bias is not None
@@ -258,13 +292,13 @@ class PerSampleConv1x1Fn(torch.autograd.Function):
     """1x1x1 conv with per-sample weights ``w[B,Cout,Cin]`` / bias ``b[B,Cout]`` (expert-mixed reduce_channels)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, pro=None):
         x = as_vol(x)
         B, Cout, Cin = w.shape
         wp = w.detach().to(x.dtype).reshape(B, 1, Cout, Cin).contiguous()
         bb = None if b is None else b.detach().float().contiguous()
-        y, _ = conv_raw(x, wp, bb, ksize=1, w_bstride=Cout * Cin, bias_bstride=Cout if b is not None else 0,
-                        impl=L.IMPL_SIMT)
+        y, _ = conv_raw(pro if pro is not None else x, wp, bb, ksize=1, w_bstride=Cout * Cin,
+                        bias_bstride=Cout if b is not None else 0, impl=L.IMPL_SIMT)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         return y
@@ -282,7 +316,7 @@ class PerSampleConv1x1Fn(torch.autograd.Function):
             dw = torch.stack([wgrad_raw(dy[i:i + 1], x[i:i + 1], ksize=1, stride=1)[0] for i in range(B)])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = channel_sums(dy)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -74,11 +74,22 @@ typedef struct {
   int32_t act;
   int32_t dtype;
   int32_t impl;         /* COMA_IMPL_* */
+  /* Optional input prologue (all NULL / 0 = off): the convolution reads x' = act_in(in_scale[b,ci] * x + in_shift[b,ci]) for
+   * every in-bounds input voxel (the zero padding stays zero).  A consumer conv thereby absorbs the Instance/BatchNorm +
+   * FiLM + activation that follows its producer (MONAI ADN, attn_unet_data_parallel.py:285-286) and the normalised tensor
+   * is never written.  in_act is COMA_ACT_NONE / RELU / LEAKY (slope read from in_slope). */
+  const float* in_scale; /* [B, Cin] fp32 or NULL */
+  const float* in_shift; /* [B, Cin] fp32 or NULL */
+  const float* in_slope; /* device pointer to the negative slope or NULL */
+  int32_t in_act;
+  int32_t reserved0;
 } coma_conv_args;
 
 int coma_conv3d_stat_chunks(const coma_conv_args* a);
 /* 1 if the tcgen05/TMA implicit-GEMM path can take this problem (bf16, channel multiples of 16, ...) */
 int coma_conv3d_tcgen05_supported(const coma_conv_args* a);
+/* 1 if a fused kernel (not the generic CUDA-core gather) applies the input prologue of this problem */
+int coma_conv3d_prologue_supported(const coma_conv_args* a);
 int coma_conv3d_fprop(const coma_conv_args* a, coma_stream_t stream);
 /* ConvTranspose3d forward (UpBlock.up, attn_unet_data_parallel.py:120-131); same struct, transposed=1 */
 int coma_convT3d_fprop(const coma_conv_args* a, coma_stream_t stream);

@@ -407,3 +407,57 @@ def test_tcgen05_is_selected_for_hot_path_shapes():
     assert L.lib().coma_conv3d_tcgen05_supported(ctypes.byref(a)) == 1
     a32 = ops._conv_args(x.float(), wp.float(), None, y.float(), ksize=3, stride=1, transposed=False, cout_comp=32)
     assert L.lib().coma_conv3d_tcgen05_supported(ctypes.byref(a32)) == 0
+
+
+# ---- input prologue: a consumer conv applies its producer's norm + FiLM + activation on load ----------------------------
+PROLOGUE_CASES = [
+    # (B, Cin, Cout, D, H, W, k, in_act, fused path expected)
+    (2, 16, 16, 20, 32, 24, 3, "leaky", True),      # modulator stack shape: v3 plane-ring kernel, 3 CTAs / SM, 32B swizzle
+    (1, 32, 32, 9, 17, 13, 3, "relu", True),        # ragged tiles, 64B swizzle, 2 CTAs / SM
+    (3, 16, 32, 6, 16, 8, 3, "none", True),         # exactly one tile per plane, several samples (coefficient restaging)
+    (2, 32, 1, 16, 16, 16, 1, "leaky", True),       # reduce_channels: pointwise, one output channel
+    (1, 64, 16, 8, 16, 8, 3, "leaky", False),       # no fused kernel for this shape: materialised, same numbers
+    (1, 16, 16, 6, 6, 6, 3, "relu", False),         # planes too small for the halo kernel
+]
+
+
+@pytest.mark.parametrize("case", PROLOGUE_CASES)
+def test_conv_input_prologue_matches_materialised_input(case):
+    import ctypes
+    B, Cin, Cout, D, H, W, k, act_name, fused = case
+    act = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "leaky": L.ACT_LEAKY}[act_name]
+    dtype = torch.bfloat16
+    x = rnd(B, Cin, D, H, W, seed=90).bfloat16().float()
+    w = rnd(Cout, Cin, k, k, k, seed=91, scale=(Cin * k ** 3) ** -0.5).bfloat16().float()
+    b = rnd(Cout, seed=92, scale=0.1)
+    A = (0.5 + torch.rand(B, Cin, generator=torch.Generator().manual_seed(93))).to(DEV)
+    S = rnd(B, Cin, seed=94, scale=0.5)
+    slope = torch.full((1,), 0.2, device=DEV)
+    u = x * A[:, :, None, None, None] + S[:, :, None, None, None]
+    xin = {"none": u, "relu": torch.relu(u), "leaky": torch.where(u > 0, u, 0.2 * u)}[act_name]
+    ref = F.conv3d(xin.bfloat16().float(), w, b, padding=(k - 1) // 2)      # the materialised tensor is bf16 too
+    xv = to_vol(x, dtype)
+    if k == 1 and Cout == 1:        # per-sample weights, like reduce_channels
+        wp = w.reshape(1, 1, Cout, Cin).expand(B, 1, Cout, Cin).contiguous().to(dtype)
+        kw = dict(w_bstride=Cout * Cin, bias_bstride=0, impl=L.IMPL_SIMT)
+        bias = b
+    else:
+        wp = ops.pack_weight(w, False, Cin, Cout, dtype)
+        kw, bias = {}, b
+    pro = ops.Deferred(xv, A, S, act, slope if act == L.ACT_LEAKY else None)
+    probe_y = torch.empty(B, D, H, W, Cout, device=DEV, dtype=dtype)
+    a = ops._conv_args(xv, wp, None, probe_y, ksize=k, stride=1, transposed=False, cout_comp=Cout,
+                       w_bstride=kw.get("w_bstride", 0), impl=kw.get("impl", L.IMPL_AUTO))
+    a.in_scale, a.in_shift, a.in_act = L.ptr(A), L.ptr(S), act
+    a.in_slope = L.ptr(slope) if act == L.ACT_LEAKY else None
+    assert bool(L.lib().coma_conv3d_prologue_supported(ctypes.byref(a))) == fused
+    y, st = ops.conv_raw(pro, wp, bias, ksize=k, want_stats=True, **kw)
+    assert err(to_ncdhw(y), ref) < 1.5e-2
+    # against the same conv on the materialised input (same kernel family, so only the bf16 rounding point differs)
+    ym, stm = ops.conv_raw(pro.materialize(), wp, bias, ksize=k, want_stats=True, **kw)
+    assert err(y.float(), ym.float()) < 1.5e-2
+    assert err(st.sum(dim=1), stm.sum(dim=1)) < 5e-3
+    # the exact CUDA-core reference implementation of the prologue
+    if not (k == 1 and Cout == 1):
+        ys, _ = ops.conv_raw(pro, wp, bias, ksize=k, impl=L.IMPL_SIMT)
+        assert err(y.float(), ys.float()) < 1.5e-2
