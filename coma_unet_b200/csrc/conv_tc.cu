@@ -1506,7 +1506,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   {
     // two CTAs per SM (stride-1 v3 kernel): everything of one CTA must fit half an SM (shared memory, 256 TMEM columns)
     static const bool two_off = [] { const char* e = getenv("COMA_DISABLE_HALO_2CTA"); return e && e[0] == '1'; }();
-    const size_t half = (h.NT == 16 ? 54 : 110) * 1024;      // NT = 16: four CTAs per SM
+    const size_t half = (h.NT == 16 ? 72 : 110) * 1024;      // NT = 16: three CTAs per SM
     const size_t tail2 = halo_tail_bytes(h.NT);
     const size_t fixed2 = 1024 + ((27u * h.KCH * h.NT * h.rowb + 1023u) & ~1023u) + tail2;
     if (!two_off && use_v3 && !h.s2 && h.KCH == 1 && h.NT <= 32 && kRing * h.NT <= 256 && fixed2 + 4 * (size_t)h.slab_bytes <= half) {
@@ -1524,7 +1524,7 @@ HaloPlan plan_halo(const coma_conv_args& a) {
   h.cols_w = (gw + HW_T - 1) / HW_T;
   h.cols_h = (gh + HH_T - 1) / HH_T;
   const int ncols = a.B * h.cols_w * h.cols_h;
-  int segs = (4 * num_sms() * h.ctas * (h.ctas == 2 && h.NT == 16 ? 4 : 2) / 2 + ncols - 1) / ncols;
+  int segs = (4 * num_sms() * h.ctas * (h.ctas == 2 && h.NT == 16 ? 3 : 2) / 2 + ncols - 1) / ncols;
   const int max_segs = (gd + 3) / 4;
   if (segs > max_segs) segs = max_segs;
   if (segs < 1) segs = 1;
@@ -1561,7 +1561,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
       cudaFuncSetAttribute(convT_halo_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, KCH, (NT <= 32 ? 2 : 1), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if constexpr (KCH == 1 && NT <= 32) cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, 1, 1, (NT == 16 ? 4 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if constexpr (KCH == 1 && NT <= 32) cudaFuncSetAttribute(conv_halo3_kernel<NT, KC, 1, 1, (NT == 16 ? 3 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (KCH == 1) cudaFuncSetAttribute(conv_halo_s2_kernel<NT, KC, (NT <= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
@@ -1581,7 +1581,7 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
   }
   else if (KCH == 1 && NT <= 32 && h.ctas == 2) {
    if constexpr (KCH == 1 && NT <= 32) {
-    constexpr int CPS = NT == 16 ? 4 : 2;
+    constexpr int CPS = NT == 16 ? 3 : 2;
     int grid2 = CPS * num_sms() / nsplit;
     if (grid2 < 1) grid2 = 1;
     if (grid2 > p.total_segs) grid2 = p.total_segs;
