@@ -30,6 +30,61 @@ def covariate_matrix(covariate, like):
     return covariate.reshape(covariate.shape[0], -1).to(device=like.device, dtype=torch.float32)
 
 
+class FilmBatch:
+    """All FiLM MLPs of a model evaluated in two batched GEMMs (no-grad paths).
+
+    Per conditioned layer the reference's module would run Linear -> ReLU -> Linear on a ``[B, num_covars]`` matrix: ~8 tiny
+    kernels x ~14 layers on the critical stream.  The MLPs only depend on the covariates, so ``compute`` evaluates them
+    all at once from stacked, zero-padded weights (columns beyond a layer's ``num_covars`` and rows beyond its ``2*Cout``
+    are zero) and ``CondConvolution.forward`` picks its ``(dgamma, beta)`` slice up from ``active``.
+    """
+
+    active: dict = {}
+
+    def __init__(self, model):
+        self.mods = [m for m in model.modules() if isinstance(m, CondConvolution) and m.film is not None]
+        self._key, self._w = None, None
+
+    def _stacked(self, device):
+        params = [p for m in self.mods for p in m.film.parameters()]
+        key = (str(device),) + tuple((p._version, p.data_ptr()) for p in params)
+        if key != self._key:
+            L = len(self.mods)
+            nmax = max(m.num_covars for m in self.mods)
+            cmax = max(m.out_channels for m in self.mods)
+            W1 = torch.zeros(L, nmax, FILM_HIDDEN, device=device)
+            b1 = torch.zeros(L, 1, FILM_HIDDEN, device=device)
+            W2 = torch.zeros(L, FILM_HIDDEN, 2 * cmax, device=device)
+            b2 = torch.zeros(L, 1, 2 * cmax, device=device)
+            with torch.no_grad():
+                for l, m in enumerate(self.mods):
+                    c = m.out_channels
+                    W1[l, :m.num_covars] = m.film[0].weight.t()
+                    b1[l, 0] = m.film[0].bias
+                    W2[l, :, :c] = m.film[2].weight[:c].t()
+                    W2[l, :, cmax:cmax + c] = m.film[2].weight[c:].t()
+                    b2[l, 0, :c] = m.film[2].bias[:c]
+                    b2[l, 0, cmax:cmax + c] = m.film[2].bias[c:]
+            self._key, self._w = key, (W1, b1, W2, b2, nmax, cmax)
+        return self._w
+
+    def compute(self, covariate):
+        """covariate: ``[B,1,n]`` / ``[B,n]`` float32 on the device.  Fills ``FilmBatch.active`` for the coming forward."""
+        if not self.mods:
+            return
+        W1, b1, W2, b2, nmax, cmax = self._stacked(covariate.device)
+        c = covariate.reshape(covariate.shape[0], -1)[:, :nmax]
+        L = len(self.mods)
+        hid = torch.relu(torch.baddbmm(b1, c.unsqueeze(0).expand(L, -1, -1), W1))        # [L, B, 64]
+        out = torch.baddbmm(b2, hid, W2)                                                  # [L, B, 2*cmax]
+        FilmBatch.active = {id(m): (out[l, :, :m.out_channels], out[l, :, cmax:cmax + m.out_channels])
+                            for l, m in enumerate(self.mods)}
+
+    @staticmethod
+    def clear():
+        FilmBatch.active = {}
+
+
 class ExpertConv3d(nn.Module):
     """Parameter container: E stacked conv kernels ``[E,Cout,Cin,k,k,k]`` and biases ``[E,Cout]``."""
 
@@ -86,7 +141,9 @@ class CondConvolution(Convolution):
             return y
         film = None
         if self.film is not None and c is not None:
-            film = self.film(c).chunk(2, dim=-1)
+            film = FilmBatch.active.get(id(self)) if not torch.is_grad_enabled() else None
+            if film is None or film[0].shape[0] != c.shape[0]:
+                film = self.film(c).chunk(2, dim=-1)
         return super().forward(x, film=film, out=out, defer=defer)
 
 

@@ -165,16 +165,33 @@ class ObservableAttentionUnet(nn.Module):
         self.compute_dtype = dtype
         return self
 
+    def _film_batch(self, covariate):
+        """No-grad forward: evaluate every FiLM MLP up front in two batched GEMMs (cond_conv.FilmBatch)."""
+        if covariate is None or torch.is_grad_enabled() or not self.conditional:
+            return False
+        fb = getattr(self, "_fb", None)
+        if fb is None:
+            fb = self._fb = cond_conv.FilmBatch(self)
+        if covariate.shape[-1] < max((m.num_covars for m in fb.mods), default=0):
+            return False
+        fb.compute(covariate)
+        return True
+
     def _backbone(self, xv, covariate, defer=False):
         """NDHWC in, NDHWC out: (x[B,D,H,W,out], encoder tensors, decoder tensors).  ``defer``: the last decoder tensor is only
         consumed by reduce_channels, whose input prologue applies its InstanceNorm/FiLM/PReLU (decs[0] is then an ops.Deferred)."""
         head, encdec, reduce_channels = self.model
-        if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1:
-            # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the tensor-core path
-            xv = ops.Pack2Fn.apply(xv, None, None, 16)
-        h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
-        d, encs, decs = encdec(h, covariate, defer_out=defer)
-        return reduce_channels(d, covariate=covariate), encs, decs
+        batched = self._film_batch(covariate)
+        try:
+            if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1:
+                # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the tensor-core path
+                xv = ops.Pack2Fn.apply(xv, None, None, 16)
+            h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
+            d, encs, decs = encdec(h, covariate, defer_out=defer)
+            return reduce_channels(d, covariate=covariate), encs, decs
+        finally:
+            if batched:
+                cond_conv.FilmBatch.clear()
 
     def forward(self, x, covariate=None):
         if covariate is not None:
