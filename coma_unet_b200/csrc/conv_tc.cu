@@ -15,6 +15,8 @@
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer +
 // TMEM allocator, warps 2..5 = epilogue (bias, per-channel statistics partials, per-(sample,channel) affine,
 // activation, bf16 store).  Two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cstdio>
+#include <type_traits>
 #include <cuda.h>
 
 #include <mutex>
@@ -74,6 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (spin > (1u << 26)) __trap();   // watchdog: a lost TMA / MMA completion must not hang the GPU
   }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -1412,6 +1420,222 @@ conv_halo_s2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 
+// ================================================================================================
+// Tap-packed kernel for the few-channel first layers (head conv on the 1-channel MRI, the modulator stacks on the 3-channel
+// painted prompt and the 2-channel [prompt | backbone] pair; attn_unet_data_parallel.py:285-286,553-556,651).
+// Padding 1-3 channels to 16 makes every tap a K = 16 MMA that is 6-19 % real work and forces a 16-channel copy of the
+// input through HBM.  Here K runs over (tap, channel): k = tap * Cin + ci, K = 27 * Cin padded to a multiple of 32, so a
+// 128-voxel tile costs 2-8 MMAs instead of 10-12 and the input is read in its own few-channel layout.
+// Input planes arrive by TMA as un-swizzled 18 x (24 Cin) slabs (the (w, c) axes merged so a row is >= 48 bytes; zero fill
+// outside the volume = padding) into a ring that keeps three planes live.  Eight builder warps (two threads per tile row:
+// taps 0..15 / 16..26) gather each voxel's neighbourhood from the slabs with constant-offset shared-memory loads and write
+// the A tile [128 rows][32 k] per K chunk in the 64B-swizzled K-major layout of the UMMA descriptor, fence the generic-proxy
+// writes and hand the stage to the MMA warp.  The B tiles are built once per CTA from the standard packed weights
+// w[tap][Cout][Cin].  Accumulator ring, segment walk and epilogue are the plane-ring ones (ring_epilogue).
+// Measured (8 x 128^3): 2->16 0.60 ms, 4->16 0.67 ms against 0.38 ms for the zero-padded 16->16 plane-ring kernel plus ~0.15 ms
+// of extra pack traffic: the ~1200 builder warp-instructions per tile make the SM issue-bound, so this kernel serves callers
+// that hold few-channel tensors (no 16-channel copy in HBM) while the model keeps padding its small inputs (model.slim_inputs).
+// ================================================================================================
+constexpr int kTapStages = 4, kTapBuilderWarps = 8, kTapSlabs = 8, kTapEpi = 1;
+constexpr int kTapThreads = 64 + 128 * kTapEpi + 32 * kTapBuilderWarps;
+
+template <int NT, int CIN>
+__global__ void __launch_bounds__(kTapThreads, 1)
+conv_taps_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ w, const HaloParams p) {
+  constexpr int K = 27 * CIN, CH = (K + 31) / 32;                        // K chunks of 32 elements (64-byte rows)
+  constexpr uint32_t A_CHUNK = 128u * 64u, A_STAGE = A_CHUNK * CH, B_CHUNK = (uint32_t)NT * 64u;
+  // slab row: 24 voxels x CIN bf16 starting at w0 - 8 (TMA needs a 16-byte aligned start in the innermost dimension, so the
+  // one-voxel halo on the low side costs seven unused voxels), un-swizzled
+  constexpr uint32_t SROW = 48u * CIN, SLAB = ((uint32_t)HALO_H * SROW + 127u) & ~127u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;                                                   // [CH][NT rows][64 B], swizzled
+  uint8_t* astg = smem + ((B_CHUNK * CH + 1023u) & ~1023u);               // [kTapStages][CH][128 rows][64 B], swizzled
+  uint8_t* slabs = astg + (size_t)kTapStages * A_STAGE;                   // [kTapSlabs][18 rows][SROW]
+  uint64_t* afull = reinterpret_cast<uint64_t*>(slabs + (size_t)kTapSlabs * SLAB);
+  uint64_t* aempty = afull + kTapStages;
+  uint64_t* sfull = aempty + kTapStages;
+  uint64_t* sempty = sfull + kTapSlabs;
+  uint64_t* tfull = sempty + kTapSlabs;
+  uint64_t* tempty = tfull + kRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kRing);
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTapStages; ++s) { mbar_init(&afull[s], kTapBuilderWarps); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < kTapSlabs; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], kTapBuilderWarps); }
+    for (int a = 0; a < kRing; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // B tiles: element (co, k) of chunk c sits at row co, byte (k%32)*2, 16-byte piece index XOR ((co >> 1) & 3)
+  for (int i = threadIdx.x; i < CH * NT * 32; i += blockDim.x) {
+    const int k = (i / (NT * 32)) * 32 + (i % 32), co = (i / 32) % NT;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (k < K && co < p.Cout) v = w[((size_t)(k / CIN) * p.Cout + co) * CIN + (k % CIN)];     // standard packed w[tap][Cout][Cin]
+    const uint32_t kb = (uint32_t)(k % 32) * 2u;
+    const uint32_t off = (uint32_t)(k / 32) * B_CHUNK + (uint32_t)co * 64u + ((((kb >> 4) ^ ((uint32_t)co >> 1)) & 3u) << 4) + (kb & 15u);
+    *reinterpret_cast<__nv_bfloat16*>(wreg + off) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer: planes d0-1 .. d0+nd of every segment =================================
+    if (lane == 0) {
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+        const SegCoord sc = decode_seg(p, t);
+        for (int pi = 0; pi < sc.nd + 2; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          mbar_expect_tx(&sfull[slot], (uint32_t)HALO_H * SROW);
+#ifndef TAPS_NO_TMA
+          tma_load_4d(slabs + (size_t)slot * SLAB, &tmX, &sfull[slot], (sc.w0 - 8) * CIN, sc.h0 - 1, sc.d0 - 1 + pi, sc.b);
+#else
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sfull[slot])), "r"((uint32_t)HALO_H * SROW) : "memory");
+#endif
+          if (++slot == (uint32_t)kTapSlabs) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =================================
+    const bool leader = elect_one();
+    constexpr uint32_t D_HI = ((8u * 64u) >> 4) | (1u << 14) | (4u << 29);          // SBO = 8 rows of 64 B, version 1, 64B swizzle
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+    const uint32_t a_lo0 = ((smem_u32(astg) & 0x3FFFFu) >> 4) | 0x10000u;
+    uint32_t stage = 0, sph = 0, s_seg = 0, pbits = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      for (int i = 0; i < sc.nd; ++i) {
+        const uint32_t blk = (s_seg + (uint32_t)(kRing * 64 - i)) & (kRing - 1);
+        mbar_wait(&afull[stage], sph);
+        mbar_wait(&tempty[blk], ((pbits >> blk) & 1u) ^ 1u);
+        pbits ^= 1u << blk;
+        tc_fence_after();
+        const uint32_t a_st = a_lo0 + stage * (A_STAGE >> 4);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint32_t a_lo = a_st + (uint32_t)c * (A_CHUNK >> 4) + (uint32_t)kk * 2u;
+            const uint32_t b_lo = w_lo + (uint32_t)c * (B_CHUNK >> 4) + (uint32_t)kk * 2u;
+            const uint32_t accum = (c | kk) != 0;
+            if (leader)
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                  "setp.ne.b32 p, %6, 0;\n\t"
+                  "mov.b64 da, {%1, %2};\n\t"
+                  "mov.b64 db, {%3, %4};\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                  ::"r"(tmem_base + blk * NT), "r"(a_lo), "r"(D_HI), "r"(b_lo), "r"(D_HI), "r"(idesc), "r"(accum)
+                  : "memory");
+          }
+        }
+        if (leader) {
+          tc_commit(&tfull[blk]);
+          tc_commit(&aempty[stage]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)kTapStages) { stage = 0; sph ^= 1u; }
+      }
+      s_seg = (s_seg + (uint32_t)(kRing * 64 - sc.nd)) & (kRing - 1);
+    }
+  } else if (warp < 2 + 4 * kTapEpi) {
+    ring_epilogue<NT, kTapEpi, 0>(p, tmem_base, tfull, tempty, sstat, 0, warp, lane);
+  } else {
+    // ================================ A-tile builders: 256 threads, two per tile row ==============
+    const int bt = (int)threadIdx.x - (64 + 128 * kTapEpi);
+    const int row = bt & 127, half = bt >> 7;                                // half 0: taps 0..15, half 1: taps 16..26 (+ zero padding)
+    const int lw = row % HW_T, lh = row / HW_T;
+    constexpr int WPT = CIN >= 2 ? CIN / 2 : 1;                              // 32-bit words per tap (CIN = 1: two taps share a word)
+    constexpr int NW = CIN == 1 ? 8 : 16 * WPT;                              // words this thread writes (taps 0..15 of its half)
+    const uint32_t voff = (uint32_t)lh * SROW + (uint32_t)lw * CIN * 2u;     // this row's voxel inside a slab (tap kh = kw = 0)
+    const uint32_t sw = ((uint32_t)row >> 1) & 3u;
+    uint32_t slot0 = 0, ph0 = 0;                                             // slab of input plane d0 - 1 + i (oldest of the three)
+    uint32_t stage = 0, aph = 0;
+    for (int t = blockIdx.x; t < p.total_segs; t += gridDim.x) {
+      const SegCoord sc = decode_seg(p, t);
+      for (int i = 0; i < sc.nd; ++i) {
+        uint32_t sl[3], sp[3];
+        sl[0] = slot0; sp[0] = ph0;
+#pragma unroll
+        for (int q = 1; q < 3; ++q) { sl[q] = sl[q - 1] + 1; sp[q] = sp[q - 1]; if (sl[q] == (uint32_t)kTapSlabs) { sl[q] = 0; sp[q] ^= 1u; } }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mbar_wait(&sfull[sl[q]], sp[q]);
+        uint32_t wd[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) wd[q] = 0u;
+        auto gather = [&](auto hsel) {            // compile-time half: every tap offset and word index is an immediate
+          constexpr int T0 = decltype(hsel)::value * 16, T1 = decltype(hsel)::value ? 27 : 16;
+#pragma unroll
+          for (int tap = T0; tap < T1; ++tap) {
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3, lt = tap - T0;
+            const uint8_t* src = slabs + (size_t)sl[kd] * SLAB + voff + (uint32_t)kh * SROW + (uint32_t)(kw + 7) * CIN * 2u;
+            if (CIN == 1) {
+              const uint32_t v = *reinterpret_cast<const uint16_t*>(src);
+              wd[lt >> 1] |= v << (16 * (lt & 1));
+            } else if (CIN == 2) {
+              wd[lt] = *reinterpret_cast<const uint32_t*>(src);
+            } else {
+              const uint2 v = *reinterpret_cast<const uint2*>(src);
+              wd[2 * lt] = v.x;
+              wd[2 * lt + 1] = v.y;
+            }
+          }
+        };
+        if (half == 0) gather(std::integral_constant<int, 0>{});
+        else gather(std::integral_constant<int, 1>{});
+        mbar_wait(&aempty[stage], aph ^ 1u);
+        uint8_t* ast = astg + (size_t)stage * A_STAGE + (size_t)row * 64u;
+        if (CIN == 1) {          // one chunk: half 0 writes 16-byte pieces 0,1 (taps 0..15), half 1 pieces 2,3
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(ast + ((((uint32_t)(2 * half + j)) ^ sw) << 4)) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
+        } else {                 // CIN/2 chunks per half (16 taps x CIN elements = CIN/2 x 32)
+#pragma unroll
+          for (int c = 0; c < CIN / 2; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(ast + (size_t)(half * (CIN / 2) + c) * A_CHUNK + (((uint32_t)j ^ sw) << 4)) =
+                  make_uint4(wd[c * 16 + j * 4], wd[c * 16 + j * 4 + 1], wd[c * 16 + j * 4 + 2], wd[c * 16 + j * 4 + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&afull[stage]);
+          // the slab reads fed the stores above, so they are complete: the oldest plane is not needed after this tile,
+          // the last tile of a segment also releases the other two
+          mbar_arrive(&sempty[sl[0]]);
+          if (i == sc.nd - 1) { mbar_arrive(&sempty[sl[1]]); mbar_arrive(&sempty[sl[2]]); }
+        }
+        if (++stage == (uint32_t)kTapStages) { stage = 0; aph ^= 1u; }
+        if (++slot0 == (uint32_t)kTapSlabs) { slot0 = 0; ph0 ^= 1u; }
+      }
+      // the segment consumed nd + 2 slabs
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (++slot0 == (uint32_t)kTapSlabs) { slot0 = 0; ph0 ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1446,7 +1670,7 @@ bool make_map(CUtensorMap* out, void* base, int rank, const cuuint64_t* dims, co
   if (it != g_map_cache.end()) { *out = it->second; return true; }
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return false; }
-  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swz == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_32B));
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return false; }
@@ -1600,6 +1824,73 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 }  // namespace
 
+// ---- tap-packed kernel (few input channels) ----
+struct TapsPlan { bool ok; int cols_w, cols_h, segs_d, DS; size_t smem; };
+
+static TapsPlan plan_taps(const coma_conv_args& a) {
+  TapsPlan t{};
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_TAPS"); return e && e[0] == '1'; }();
+  if (off || a.transposed || a.ksize != 3 || a.stride != 1 || a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return t;
+  if (!(a.Cin == 1 || a.Cin == 2 || a.Cin == 4) || a.x_cs != a.Cin || a.x_co != 0 || a.in_scale) return t;
+  if (!(a.Cout == 16 || a.Cout == 32) || a.act == COMA_ACT_SIGMOID) return t;
+  if (a.Wo < HW_T || a.Ho < HH_T) return t;
+  if (reinterpret_cast<uintptr_t>(a.x) % 16 != 0 || (a.Wi * a.Cin) % 8 != 0) return t;      // TMA: 16-byte base and row pitch
+  const int ch = (27 * a.Cin + 31) / 32;
+  const size_t slab = ((size_t)HALO_H * 48 * a.Cin + 127) & ~(size_t)127;
+  t.smem = 1024 + (((size_t)a.Cout * 64 * ch + 1023) & ~(size_t)1023) + (size_t)kTapStages * 128 * 64 * ch + kTapSlabs * slab +
+           (2 * kTapStages + 2 * kTapSlabs + 2 * kRing) * 8 + 16 + (size_t)22 * a.Cout * sizeof(float) + 64;
+  if (t.smem > 222 * 1024) return t;
+  t.cols_w = (a.Wo + HW_T - 1) / HW_T;
+  t.cols_h = (a.Ho + HH_T - 1) / HH_T;
+  const int ncols = a.B * t.cols_w * t.cols_h;
+  int segs = (4 * num_sms() + ncols - 1) / ncols;
+  const int max_segs = (a.Do + 3) / 4;
+  if (segs > max_segs) segs = max_segs;
+  if (segs < 1) segs = 1;
+  t.DS = (a.Do + segs - 1) / segs;
+  t.segs_d = (a.Do + t.DS - 1) / t.DS;
+  t.ok = true;
+  return t;
+}
+
+template <int NT, int CIN>
+static int launch_taps(const coma_conv_args& a, const TapsPlan& t, cudaStream_t stream) {
+  HaloParams p{};
+  p.B = a.B; p.D = a.Do; p.H = a.Ho; p.W = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout;
+  p.cols_w = t.cols_w; p.cols_h = t.cols_h; p.segs_d = t.segs_d; p.DS = t.DS;
+  p.total_segs = a.B * t.cols_w * t.cols_h * t.segs_d;
+  p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
+  p.stat_chunks = t.cols_w * t.cols_h * t.segs_d * kTapEpi;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)kRing * NT) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(conv_taps_kernel<NT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  int grid = num_sms();
+  if (grid > p.total_segs) grid = p.total_segs;
+  CUtensorMap tmX;
+  {   // (w, c) merged so that a slab row is >= 32 bytes: [B, D, H, W*Cin], box 16 voxels x 18 rows of one plane
+    cuuint64_t dims[4] = {(cuuint64_t)a.Wi * CIN, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.Wi * CIN * 2, (cuuint64_t)a.Hi * a.Wi * CIN * 2, (cuuint64_t)a.Di * a.Hi * a.Wi * CIN * 2};
+    cuuint32_t box[4] = {24u * CIN, (cuuint32_t)HALO_H, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!make_map(&tmX, const_cast<void*>(a.x), 4, dims, strides, box, estr, 0)) return COMA_ERR_CUDA;
+  }
+  conv_taps_kernel<NT, CIN><<<grid, kTapThreads, t.smem, stream>>>(tmX, static_cast<const __nv_bfloat16*>(a.w), p);
+  COMA_CHECK_LAUNCH("conv_taps");
+  return COMA_OK;
+}
+
+static int conv_taps_launch(const coma_conv_args& a, const TapsPlan& t, cudaStream_t stream) {
+#define COMA_TAPS_CASE(NTV, CV) if (a.Cout == NTV && a.Cin == CV) return launch_taps<NTV, CV>(a, t, stream);
+  COMA_TAPS_CASE(16, 1) COMA_TAPS_CASE(16, 2) COMA_TAPS_CASE(16, 4)
+  COMA_TAPS_CASE(32, 1) COMA_TAPS_CASE(32, 2) COMA_TAPS_CASE(32, 4)
+#undef COMA_TAPS_CASE
+  set_error("conv_taps: unsupported channel combination");
+  return COMA_ERR_UNSUPPORTED;
+}
+
 // the input prologue lives in the stride-1 plane-ring kernel (one K chunk): everything else declines it
 bool conv_tc_prologue_supported(const coma_conv_args& a) {
   if (!a.in_scale) return true;
@@ -1613,6 +1904,7 @@ bool conv_tc_prologue_supported(const coma_conv_args& a) {
 
 bool conv_tc_supported(const coma_conv_args& a) {
   if (a.in_scale && !conv_tc_prologue_supported(a)) return false;
+  if (plan_taps(a).ok) return true;
   if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
   if (a.act == COMA_ACT_SIGMOID) return false;   // epilogue: relu-family activations only
   if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;
@@ -1628,6 +1920,10 @@ static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int&
 }
 
 int conv_tc_stat_chunks(const coma_conv_args& a) {
+  {
+    const TapsPlan t = plan_taps(a);
+    if (t.ok) return t.cols_w * t.cols_h * t.segs_d * kTapEpi;
+  }
   const HaloPlan h = plan_halo(a);
   if (h.ok) {
     static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
@@ -1673,6 +1969,10 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
 }
 
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
+  {
+    const TapsPlan t = plan_taps(a);
+    if (t.ok) return conv_taps_launch(a, t, stream);
+  }
   {
     const HaloPlan h = plan_halo(a);
     if (h.ok) return conv_halo_launch(a, h, stream);

@@ -38,6 +38,12 @@ __global__ void __launch_bounds__(256) roi_paint_kernel(coma_roi_paint_args a) {
       store8(o, vals);
       const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int c = 8; c < a.out_cs; c += 8) store8(o + c, zeros);
+    } else if (sizeof(T) == 2 && a.out_cs == 4) {   // [prompt, saliency, suvr, 0] as one 8-byte store (tap-packed consumer conv)
+      const __nv_bfloat162 p01 = __floats2bfloat162_rn(__ldg(prompt + v), sd), p23 = __floats2bfloat162_rn(loc, 0.f);
+      uint2 q;
+      q.x = *reinterpret_cast<const uint32_t*>(&p01);
+      q.y = *reinterpret_cast<const uint32_t*>(&p23);
+      *reinterpret_cast<uint2*>(o) = q;
     } else {
       Elem<T>::st(o, __ldg(prompt + v));
       if (a.out_cs > 1) Elem<T>::st(o + 1, sd);
@@ -91,6 +97,9 @@ __global__ void __launch_bounds__(256) pack2_kernel(coma_pack2_args a) {
         store8(o, vals);
         const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int c = 8; c < a.dst_cs; c += 8) store8(o + c, zeros);
+      } else if (sizeof(T) == 2 && a.dst_cs == 2) {
+        const __nv_bfloat162 pr = __floats2bfloat162_rn(va[u], vbv[u]);
+        *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(&pr);
       } else {
         Elem<T>::st(o, va[u]);
         Elem<T>::st(o + 1, vbv[u]);

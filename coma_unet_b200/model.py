@@ -183,8 +183,10 @@ class ObservableAttentionUnet(nn.Module):
         head, encdec, reduce_channels = self.model
         batched = self._film_batch(covariate)
         try:
-            if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1:
-                # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the tensor-core path
+            if xv.dtype == torch.bfloat16 and xv.shape[-1] == 1 and not (
+                    getattr(self, "slim_inputs", False) and not torch.is_grad_enabled() and ops.taps_conv_ok(xv)):
+                # 1 -> 16 zero-padded input channels: the Cin=1 head conv then takes the plane-ring tensor-core path.
+                # ``slim_inputs`` (off: measured slower, see conv_taps_kernel) feeds the 1-channel volume to the tap-packed kernel.
                 xv = ops.Pack2Fn.apply(xv, None, None, 16)
             h = head(xv, covariate=covariate[:, :, :5] if covariate is not None else None)
             d, encs, decs = encdec(h, covariate, defer_out=defer)
@@ -314,10 +316,13 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
             if flags is None:
                 flags = (cov0 == 1).cpu()
             used = (bool(flags.any()), bool((~flags).any()))
+        # channel padding of the two small inputs: 16 for the per-tap tensor-core path; without autograd the tap-packed
+        # kernel takes them as 4 (3 + one zero) and 2 channels
+        slim = getattr(self, "slim_inputs", False) and not torch.is_grad_enabled() and dt == torch.bfloat16 and ops.taps_conv_ok(out)
         painted = ops.RoiPaintFn.apply(self.pos_dynamic_prompt, self.neg_dynamic_prompt, sample_roi_mask, x, lut,
-                                       self._roi_ids, is_pos, self.PAD, dt, used)
+                                       self._roi_ids, is_pos, 4 if slim else self.PAD, dt, used)
         m1 = self.deep_modulator_3c(painted)                                           # [B,D,H,W,1]
-        packed = ops.Pack2Fn.apply(m1, self.general_dynamic_prompt, out, self.PAD)     # [general + m1 | out | 0..]
+        packed = ops.Pack2Fn.apply(m1, self.general_dynamic_prompt, out, 2 if slim else self.PAD)   # [general + m1 | out | 0..]
         fused = self.fusion_layer(packed)                                              # [B,D,H,W,1]
         pair = ops.Pack2Fn.apply(out, None, fused, 2)                                  # [out | fused]
         return self.final_pred_head(pair, final_relu=True)                             # conv1x1 + IN + PReLU, then ReLU

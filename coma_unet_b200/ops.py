@@ -145,6 +145,11 @@ class Deferred:
         return affine_act(self.raw, self.A, self.S, self.slope, self.act, out=out)
 
 
+def taps_conv_ok(x) -> bool:
+    """The tap-packed few-channel conv kernel needs planes of at least 16 x 8 voxels (bf16)."""
+    return x.dtype == torch.bfloat16 and x.shape[2] >= 16 and x.shape[3] >= 8
+
+
 def materialized(x):
     return x.materialize() if isinstance(x, Deferred) else x
 

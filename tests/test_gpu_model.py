@@ -201,3 +201,18 @@ def test_prefetcher_and_sink_stream_batches_in_order():
     assert seen == [f"item{i}" for i in range(7)]
     # the ring holds the last `depth` results
     assert float(results[-1][0, 0, 0, 0, 0]) == 2 * 6 + 6 and float(results[-2][0, 0, 0, 0, 0]) == 2 * 5 + 5
+
+
+def test_slim_inputs_path_matches_padded_path():
+    """model.slim_inputs feeds the 1- / 3- / 2-channel tensors to the tap-packed conv kernel instead of zero-padding them
+    to 16 channels: same network, same numbers (bf16 rounding only)."""
+    torch.manual_seed(3)
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [16, 32, 64], [2, 2, 2], latent_spaces=[64] * 3, conditional=True,
+                                       prompt_shape=(32, 32, 32), compute_dtype=torch.bfloat16).cuda().eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = common.synthetic_batch(2, (32, 32, 32), 5)
+    with torch.no_grad():
+        ref = m(mri.cuda(), covars, roi_pred_dicts=dicts, sample_roi_mask=roi.cuda())
+        m.slim_inputs = True
+        got = m(mri.cuda(), covars, roi_pred_dicts=dicts, sample_roi_mask=roi.cuda())
+    assert check.scaled_err(got.cpu(), ref.cpu()) < 3e-2

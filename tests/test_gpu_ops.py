@@ -365,6 +365,11 @@ TC_CASES = [
     (1, 16, 16, 20, 32, 34, 3, 2, False),    # 32B swizzle, two epilogue warpgroups
     (1, 32, 128, 9, 32, 16, 3, 2, False),    # Cout split 2 x 64
     (3, 32, 32, 40, 64, 32, 3, 2, False),    # many segments per CTA: ring wrap and phase bookkeeping
+    # tap-packed kernel for 1 / 2 / 4 input channels (K = 27 * Cin, A tiles gathered by builder warps)
+    (2, 1, 32, 12, 32, 16, 3, 1, False),     # the head conv on the 1-channel MRI
+    (1, 2, 16, 9, 17, 12, 3, 1, False),      # ragged tiles, two K chunks (TMA needs W * Cin to be a multiple of 8)
+    (1, 4, 16, 20, 32, 24, 3, 1, False),     # four K chunks (the 3-channel painted prompt + one zero channel)
+    (3, 1, 16, 37, 16, 8, 3, 1, False),      # one tile per plane, long segments: stage and ring wrap
 ]
 
 
