@@ -422,8 +422,80 @@ __global__ void __launch_bounds__(256) wgrad_cg1_kernel(coma_wgrad_args a, int64
   }
 }
 
+
+// One-channel gradient (the 16 -> 1 modulator heads), k3 s1: walk the x voxels ONCE per kd plane instead of once per tap.
+// A thread owns one 8-channel vector of an x voxel and accumulates its contribution to the nine (kh,kw) taps of its kd:
+// dw[kd,kh,kw][c] += x[i][c] * g[i - k + 1]; the 72 partial sums are reduced per block and added atomically.
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_cg1_k3s1_kernel(coma_wgrad_args a, int64_t vchunk) {
+  const int kd = blockIdx.y;
+  const int CV = a.Cx >> 3, cvec = threadIdx.x % CV, vlane = threadIdx.x / CV, lanes = 256 / CV;
+  const int64_t Vx = (int64_t)a.Dx * a.Hx * a.Wx, total = (int64_t)a.B * Vx;
+  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, total);
+  const T* gp = static_cast<const T*>(a.g) + a.g_co;
+  const T* xp = static_cast<const T*>(a.x) + a.x_co + cvec * 8;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+  for (int64_t i = begin + vlane; i < end; i += lanes) {
+    const int64_t bb = i / Vx, rem = i - bb * Vx;
+    const int iw = (int)(rem % a.Wx), t2 = (int)(rem / a.Wx);
+    const int ih = t2 % a.Hx, id = t2 / a.Hx;
+    const int od = id - kd + 1;
+    if (od < 0 || od >= a.Dg) continue;
+    float xv[8];
+    load8(xp + i * a.x_cs, xv);
+    const T* gplane = gp + ((bb * a.Dg + od) * a.Hg) * (int64_t)a.Wg * a.g_cs;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int oh = ih - kh + 1;
+      if (oh < 0 || oh >= a.Hg) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ow = iw - kw + 1;
+        if (ow < 0 || ow >= a.Wg) continue;
+        const float gv = Elem<T>::ld(gplane + ((int64_t)oh * a.Wg + ow) * a.g_cs);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[kh * 3 + kw][e] = fmaf(gv, xv[e], acc[kh * 3 + kw][e]);
+      }
+    }
+  }
+  // reduce over the voxel lanes that share a channel vector: lanes with equal (threadIdx.x % CV); CV divides 32
+  __shared__ float red[8][9][8 * 8];        // [warp][tap][cvec * 8 + e], CV <= 8
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[t][e];
+      for (int o = 16; o >= CV; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) < CV) red[threadIdx.x >> 5][t][cvec * 8 + e] = v;
+    }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 9 * a.Cx; j += 256) {
+    const int t = j / a.Cx, c = j % a.Cx;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][t][c];
+    atomicAdd(a.dw + (int64_t)(kd * 9 + t) * a.Cx + c, sum);
+  }
+}
+
 int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
+  if (a.Cg == 1 && a.ksize == 3 && a.stride == 1 && a.Cx % 8 == 0 && a.Cx <= 64 && 32 % (a.Cx / 8) == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
+    const int64_t totx = (int64_t)a.B * a.Dx * a.Hx * a.Wx;
+    int64_t want = (int64_t)num_sms() * 4 / 3;
+    int64_t vchunk = std::max<int64_t>((totx + want - 1) / want, 4096);
+    const int64_t nch = (totx + vchunk - 1) / vchunk;
+    dim3 grid((unsigned)nch, 3);
+    if (a.dtype == COMA_BF16) wgrad_cg1_k3s1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, vchunk);
+    else wgrad_cg1_k3s1_kernel<float><<<grid, 256, 0, stream>>>(a, vchunk);
+    COMA_CHECK_LAUNCH("wgrad_cg1_k3s1");
+    return COMA_OK;
+  }
   if (a.Cg == 1 && a.Cx <= 64) {
     const int taps = a.ksize * a.ksize * a.ksize;
     int64_t want = (int64_t)num_sms() * 8 / taps;

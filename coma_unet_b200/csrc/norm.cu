@@ -25,10 +25,14 @@ struct BwdCtx {
   const void* r; int r_cs;   // optional residual added before the activation: u = A*x + S + r
 };
 
-template <typename T, int NQ>
+// SIMPLE: act in {none, relu, leaky/prelu}: d act/du = u > 0 ? 1 : gneg, d act/d slope = leaky ? min(u, 0) : 0 -- no per-element
+// dispatch on the activation code (the switch made these sweeps instruction- rather than HBM-bound)
+template <typename T, int NQ, bool SIMPLE>
 __device__ __forceinline__ void accumulate8(const float (&xv)[8], const float (&dyv)[8], const float (&rv)[8], const float* A8,
                                             const float* S8, const float* M8, const float* R8, int act, float slope,
                                             float (&acc)[8][NQ]) {
+  const float gneg = act == COMA_ACT_NONE ? 1.f : (act == COMA_ACT_RELU ? 0.f : slope);
+  const float sflag = act == COMA_ACT_LEAKY ? 1.f : 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     if (NQ == 2) {
@@ -36,15 +40,15 @@ __device__ __forceinline__ void accumulate8(const float (&xv)[8], const float (&
       acc[e][1] += xv[e] * xv[e];
     } else {
       const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
-      const float dz = dyv[e] * act_grad(act, u, slope);
+      const float dz = dyv[e] * (SIMPLE ? (u > 0.f ? 1.f : gneg) : act_grad(act, u, slope));
       acc[e][0] += dz;
       acc[e][1] += dz * (xv[e] - M8[e]) * R8[e];
-      if (NQ > 2) acc[e][NQ - 1] += dyv[e] * act_slope_grad(act, u, slope);
+      if (NQ > 2) acc[e][NQ - 1] += SIMPLE ? sflag * dyv[e] * fminf(u, 0.f) : dyv[e] * act_slope_grad(act, u, slope);
     }
   }
 }
 
-template <typename T, int NQ>
+template <typename T, int NQ, bool SIMPLE>
 __global__ void __launch_bounds__(kThreads) reduce_vec_kernel(const T* __restrict__ x, int64_t V, int C, int cs, int co,
                                                               int chunks, float* __restrict__ partial, BwdCtx ctx) {
   extern __shared__ float red[];  // [kThreads][8*NQ]
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) reduce_vec_kernel(const T* __restric
       load8(xb + v * cs, xv);
       if (NQ == 3) load8(dyb + v * ctx.dy_cs, dyv);
       if (NQ == 3 && rb) load8(rb + v * ctx.r_cs, rv);
-      accumulate8<T, NQ>(xv, dyv, rv, A8, S8, M8, R8, ctx.act, slope, acc);
+      accumulate8<T, NQ, SIMPLE>(xv, dyv, rv, A8, S8, M8, R8, ctx.act, slope, acc);
     }
   }
 #pragma unroll
@@ -159,7 +163,9 @@ static int launch_reduce(const void* x, int B, int64_t V, int C, int cs, int co,
   if (NQ == 3) v = v && vec_ok(ctx.dy, C, ctx.dy_cs, ctx.dy_co, dtype) && (!ctx.r || vec_ok(ctx.r, C, ctx.r_cs, 0, dtype));
   if (v) {
     const size_t smem = (size_t)kThreads * 8 * NQ * sizeof(float);
-    reduce_vec_kernel<T, NQ><<<grid, kThreads, smem, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
+    const bool simple = NQ == 3 && (ctx.act == COMA_ACT_NONE || ctx.act == COMA_ACT_RELU || ctx.act == COMA_ACT_LEAKY);
+    if (simple) reduce_vec_kernel<T, NQ, true><<<grid, kThreads, smem, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
+    else reduce_vec_kernel<T, NQ, false><<<grid, kThreads, smem, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
   } else {
     COMA_CHECK_ARG(C <= 8, "norm reduce: C=%d must be a power-of-two multiple of 8 (aligned) or <= 8", C);
     reduce_small_kernel<T, NQ><<<grid, kThreads, 0, stream>>>(static_cast<const T*>(x), V, C, cs, co, chunks, partial, ctx);
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(coma_affine_act_
   }
 }
 
-template <typename T>
+template <typename T, bool SIMPLE>
 __global__ void __launch_bounds__(kThreads) bwd_apply_vec_kernel(coma_affine_act_bwd_args a, int chunks) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int CV = a.C >> 3, lanes = kThreads / CV;
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_vec_kernel(coma_affine_act
     P8[e] = a.coef[i * 3]; Q8[e] = a.coef[i * 3 + 1]; R8[e] = a.coef[i * 3 + 2];
   }
   const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const float gneg = a.act == COMA_ACT_NONE ? 1.f : (a.act == COMA_ACT_RELU ? 0.f : slope);
   const T* xb = static_cast<const T*>(a.x) + (int64_t)b * a.V * a.x_cs + a.x_co + cvec * 8;
   const T* dyb = static_cast<const T*>(a.dy) + (int64_t)b * a.V * a.dy_cs + a.dy_co + cvec * 8;
   T* dxb = static_cast<T*>(a.dx) + (int64_t)b * a.V * a.dx_cs + a.dx_co + cvec * 8;
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_vec_kernel(coma_affine_act
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
-      const float dz = dyv[e] * act_grad(a.act, u, slope);
+      const float dz = dyv[e] * (SIMPLE ? (u > 0.f ? 1.f : gneg) : act_grad(a.act, u, slope));
       xv[e] = fmaf(P8[e], dz, fmaf(R8[e], xv[e], Q8[e]));
       rv[e] = dz;
     }
@@ -514,8 +521,14 @@ extern "C" int coma_norm_film_act_bwd(const coma_affine_act_bwd_args* a, coma_st
   if (vec) {
     const int ach = (int)std::min<int64_t>(std::max<int64_t>((a->V * (a->C / 8) + kThreads * 8 - 1) / (kThreads * 8), 1), 4096);
     dim3 grid((unsigned)ach, (unsigned)a->B);
-    if (a->dtype == COMA_BF16) bwd_apply_vec_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(*a, ach);
-    else bwd_apply_vec_kernel<float><<<grid, kThreads, 0, stream>>>(*a, ach);
+    const bool simple = a->act == COMA_ACT_NONE || a->act == COMA_ACT_RELU || a->act == COMA_ACT_LEAKY;
+    if (a->dtype == COMA_BF16) {
+      if (simple) bwd_apply_vec_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, stream>>>(*a, ach);
+      else bwd_apply_vec_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, stream>>>(*a, ach);
+    } else {
+      if (simple) bwd_apply_vec_kernel<float, true><<<grid, kThreads, 0, stream>>>(*a, ach);
+      else bwd_apply_vec_kernel<float, false><<<grid, kThreads, 0, stream>>>(*a, ach);
+    }
   } else {
     COMA_CHECK_ARG(a->C <= 64, "coma_norm_film_act_bwd: unaligned C=%d too large for the scalar path", a->C);
     dim3 grid((unsigned)std::min<int64_t>((a->V + kThreads - 1) / kThreads, 2048), (unsigned)a->B);

@@ -54,6 +54,8 @@ CONV_CASES = [
     (2, 32, 16, 8, 8, 8, 1, 1, False),
     (2, 16, 1, 8, 8, 8, 1, 1, False),       # psi / head convs
     (1, 3, 5, 5, 6, 7, 3, 1, False),        # odd channel counts (scalar path)
+    (2, 16, 1, 9, 10, 12, 3, 1, False),     # modulator head 16 -> 1: single-pass one-channel weight gradient
+    (1, 32, 1, 8, 8, 8, 3, 1, False),
     # >= 16^3 voxels, k3 s1, <= 64 channels: halo weight-gradient kernel (bf16) / halo forward + dgrad kernels
     (2, 16, 32, 16, 16, 16, 3, 1, False),
     (1, 32, 32, 17, 18, 20, 3, 1, False),   # ragged in every dim
