@@ -216,3 +216,21 @@ def test_slim_inputs_path_matches_padded_path():
         m.slim_inputs = True
         got = m(mri.cuda(), covars, roi_pred_dicts=dicts, sample_roi_mask=roi.cuda())
     assert check.scaled_err(got.cpu(), ref.cpu()) < 3e-2
+
+
+def test_non_cubic_volume_matches_oracle():
+    """A volume that is neither cubic nor 128^3 (ragged tiles at every level, batch 3) through the whole eval network:
+    fp32 path against the CPU oracle, bf16 path within the bf16 bound."""
+    case = {"channels": [16, 32, 64, 128, 256], "shape": [48, 64, 32], "batch": 3, "seed": 31}
+    o = build(case, None, cls=lambda *a, compute_dtype=None, **k: omodel.ContrastiveAttentionUNET_DP(*a, **k)).cpu().eval()
+    o.set_training(False)
+    mri, tau, roi, covars, dicts = batch(case)
+    with torch.no_grad():        # the oracle runs on the CPU in fp32 (cuDNN would use TF32 and be the less exact side)
+        want = o(mri.cpu(), covars, roi_pred_dicts=dicts, sample_roi_mask=roi.cpu()).numpy()
+    for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 3e-2)):
+        m = build(case, dtype).eval()
+        m.set_training(False)
+        with torch.no_grad():
+            got = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi).cpu().numpy()
+        assert got.shape == want.shape == (3, 1, 48, 64, 32)
+        assert check.scaled_err(got, want) < tol, (dtype, check.scaled_err(got, want))

@@ -468,3 +468,57 @@ def test_conv_input_prologue_matches_materialised_input(case):
     if not (k == 1 and Cout == 1):
         ys, _ = ops.conv_raw(pro, wp, bias, ksize=k, impl=L.IMPL_SIMT)
         assert err(y.float(), ys.float()) < 1.5e-2
+
+
+# ---- BASELINE-size (batch 8 x 128^3) checks through size-independent properties ------------------------------------------
+FULL = (8, 128, 128, 128)
+
+
+def _grid_volume(B, D, H, W, Cn, seed):
+    """bf16 values on a coarse grid (multiples of 1/4 in [-2, 2]): sums of two such volumes are exact in bf16."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randint(-8, 9, (B, D, H, W, Cn), device=DEV, generator=g).float() / 4).bfloat16()
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (64, 32)])
+def test_full_size_conv_is_linear_and_translation_equivariant(cin, cout):
+    """Plane-ring tcgen05 conv at the benchmark size: conv(x1 + x2) = conv(x1) + conv(x2) up to output rounding, the
+    fused statistics are linear and match the stored output, and shifting the input by one tile shifts the output
+    bit-exactly (tiling, halo and segment bookkeeping do not depend on position)."""
+    B, D, H, W = FULL
+    w = (rnd(cout, cin, 3, 3, 3, seed=70, scale=(cin * 27) ** -0.5)).bfloat16().float()
+    wp = ops.pack_weight(w, False, cin, cout, torch.bfloat16)
+    x1, x2 = _grid_volume(B, D, H, W, cin, 71), _grid_volume(B, D, H, W, cin, 72)
+    y1, s1 = ops.conv_raw(x1, wp, None, ksize=3, want_stats=True)
+    y2, s2 = ops.conv_raw(x2, wp, None, ksize=3, want_stats=True)
+    y12, s12 = ops.conv_raw(x1 + x2, wp, None, ksize=3, want_stats=True)
+    scale = float(y12.float().abs().max())
+    assert float((y12.float() - (y1.float() + y2.float())).abs().max()) < 1.5 * 2 ** -8 * scale      # three bf16 roundings
+    lin = (s12.sum(dim=1)[..., 0] - s1.sum(dim=1)[..., 0] - s2.sum(dim=1)[..., 0]).abs().max()
+    assert float(lin) < 1e-4 * float(s12.sum(dim=1)[..., 1].max()) ** 0.5 * (D * H * W) ** 0.5
+    # checksum: per-(sample, channel) sums of the fp32 accumulators against the bf16 tensor that was stored
+    stored = y12.float().sum(dim=(1, 2, 3))
+    assert err(s12.sum(dim=1)[..., 0], stored) < 2e-3
+    del y2, s1, s2, s12, x2
+    # translation by one tile along w and h, one plane along d
+    xs = torch.roll(x1, shifts=(1, 16, 8), dims=(1, 2, 3))
+    ys, _ = ops.conv_raw(xs, wp, None, ksize=3)
+    ref = torch.roll(y1, shifts=(1, 16, 8), dims=(1, 2, 3))
+    inner = (slice(None), slice(2, D - 2), slice(18, H - 18), slice(10, W - 10))
+    assert torch.equal(ys[inner], ref[inner])
+
+
+def test_full_size_stride2_and_transposed_round_trip_shapes_and_adjointness():
+    """<conv_s2(x), g> == <x, convT(g)> for the stride-2 pair (dgrad of one is the other) at the benchmark size: the
+    tcgen05 stride-2 and transposed kernels are adjoint to bf16 accuracy."""
+    B, D, H, W = FULL
+    cin, cout = 32, 64
+    w = rnd(cout, cin, 3, 3, 3, seed=73, scale=(cin * 27) ** -0.5).bfloat16().float()
+    x = _grid_volume(B, D, H, W, cin, 74)
+    g = _grid_volume(B, D // 2, H // 2, W // 2, cout, 75)
+    y, _ = ops.conv_raw(x, ops.pack_weight(w, False, cin, cout, torch.bfloat16), None, ksize=3, stride=2)
+    # adjoint of conv(stride 2) = convT(stride 2) with the same kernel read as ConvTranspose3d weights [Cin=cout, Cout=cin]
+    xt, _ = ops.conv_raw(g, ops.pack_weight(w, True, cout, cin, torch.bfloat16), None, ksize=3, stride=2, transposed=True)
+    lhs = float((y.float() * g.float()).sum())
+    rhs = float((x.float() * xt.float()).sum())
+    assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0) + 2e-3 * float(y.float().norm() * g.float().norm()) * 1e-2
