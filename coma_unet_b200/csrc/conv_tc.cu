@@ -1636,6 +1636,258 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
   }
 }
 
+// ================================================================================================
+// CTA-pair plane kernel (cta_group::2) for k3 s1 convolutions with 64 / 128 input channels.
+//
+// With Cin = 128 the 27 weight tiles of even 32 output channels (221 KB) do not fit next to two slabs, so the single-CTA
+// kernel splits Cout four ways and issues N = 3*16 = 48 MMAs that are bound by the A-operand read (44 cycles for 24 cycles
+// of math).  Two SMs of a TPC can share ONE weight set: each CTA keeps its own 128-voxel tile (own slabs, own TMEM
+// accumulators, own epilogue) and HALF of the rows of every weight tile; the leader CTA issues tcgen05.mma.cta_group::2
+// with M = 256, N = 3*32 = 96 (measured 49 cycles, profiles/r01_probe_cta_pair_mma.log: 1.8x the work per SM-cycle).
+//
+// Because the two CTAs hold fixed halves of each 96-row weight tile, every MMA must be the full N = 96: there are no
+// partial-N steps for ring wrap-around, segment edges or "first tap" initialisation.  Instead
+//   * TMEM is a LINEAR array of 16 blocks per segment (<= 12 output planes): input plane pi always adds into blocks
+//     [pi, pi+1, pi+2] through W[kd = 2, 1, 0]; blocks 0, 1 and nd+2, nd+3 only ever receive out-of-segment garbage;
+//   * every MMA accumulates; the epilogue warps clear a block (tcgen05.st) after draining it, and all blocks once at start.
+// Cross-CTA plumbing: both producers signal the LEADER's slab barrier (cp.async.bulk.tensor.cta_group::2 + remote
+// expect_tx), both epilogues arrive on the leader's accumulator-free barriers through shared::cluster addresses, and the
+// leader's tcgen05.commit multicasts "accumulator ready" / "slab free" to both CTAs.
+// ================================================================================================
+constexpr int kPairBlocks = 16, kPairMaxND = kPairBlocks - 4, kPairEpi = 2;
+constexpr int kPairThreads = 64 + 128 * kPairEpi;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(const void* local, uint32_t rank) {        // shared::cluster address of `local` in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+               ::"r"(taddr), "r"(0u) : "memory");
+}
+
+template <int NT, int KC, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  constexpr uint32_t ROWB = KC * 2u, HALF = 3u * NT / 2u;                  // weight rows per CTA and (tap, K chunk): half of [kd2|kd1|kd0] x NT
+  constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wreg = smem;                                                    // [9 (kh,kw)][KCH][HALF rows][ROWB]
+  uint8_t* slabs = smem + ((p.w_bytes + 1023u) & ~1023u);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(slabs + (size_t)p.nslab * p.slab_bytes);
+  uint64_t* sempty = sfull + kMaxSlabs;
+  uint64_t* wfull = sempty + kMaxSlabs;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + kPairBlocks;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kPairBlocks);
+  float* sstat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n0 = blockIdx.y * NT;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1, units = p.total_segs >> 1;    // a unit = two w-adjacent segments
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslab; ++s) { mbar_init(&sfull[s], 2); mbar_init(&sempty[s], 1); }      // leader: both CTAs' slabs
+    mbar_init(wfull, 1);
+    for (int a = 0; a < kPairBlocks; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }   // leader: 4 warps of each CTA
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    // this CTA's half of every weight tile: rows [HALF*rank, HALF*rank + HALF) of [kd=2 | kd=1 | kd=0] x NT, in 16-row boxes
+    mbar_expect_tx(wfull, p.w_bytes);
+    for (int t9 = 0; t9 < 9; ++t9)
+      for (int kc = 0; kc < KCH; ++kc)
+        for (uint32_t q = 0; q < HALF / 16u; ++q) {
+          const uint32_t j0 = HALF * rank + 16u * q;
+          const int kd = 2 - (int)(j0 / NT), co0 = (int)(j0 % NT);
+          tma_load_2d(wreg + (size_t)((t9 * KCH + kc) * HALF + 16u * q) * ROWB, &tmB, wfull, kc * KC, (kd * 9 + t9) * p.Cout + n0 + co0);
+        }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  mbar_wait(wfull, 0);
+  cluster_sync_all();                       // both CTAs: barriers initialised, weights resident, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs; completion is signalled on the LEADER's barrier) ==========
+    if (lane == 0) {
+      uint32_t slot = 0, ph = 0;
+      for (int u = pair; u < units; u += npairs) {
+        const SegCoord sc = decode_seg(p, 2 * u + (int)rank);
+        for (int pi = 0; pi < sc.nd + 2; ++pi) {
+          mbar_wait(&sempty[slot], ph ^ 1u);
+          const uint32_t lead_full = mapa_rank(&sfull[slot], 0);
+          mbar_expect_tx_cluster(lead_full, p.slab_tx);
+          for (int kc = 0; kc < KCH; ++kc)
+            tma_load_5d_pair(slabs + (size_t)slot * p.slab_bytes + (size_t)kc * p.chunk_bytes, &tmA, lead_full, kc * KC, sc.w0 - 1, sc.h0 - 1,
+                             sc.d0 - 1 + pi, sc.b);
+          if (++slot == (uint32_t)p.nslab) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer: leader CTA only, M = 256 over both SMs ============
+    if (rank == 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t A_HI = ((HALO_W * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+      constexpr uint32_t B_HI = ((8u * ROWB) >> 4) | (1u << 14) | (LAYOUT << 29);
+      constexpr uint32_t W_TILE16 = (HALF * ROWB) >> 4;
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((3u * NT) >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t w_lo = ((smem_u32(wreg) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t s_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t slab16 = p.slab_bytes >> 4, chunk16 = p.chunk_bytes >> 4;
+      uint32_t slot = 0, sph = 0, pbits = 0;
+      for (int u = pair; u < units; u += npairs) {
+        const SegCoord sc = decode_seg(p, 2 * u);
+        for (int pi = 0; pi < sc.nd + 2; ++pi) {
+          mbar_wait(&sfull[slot], sph);
+          // blocks this plane touches for the first time in this segment must have been drained and cleared
+          for (int b = (pi == 0 ? 0 : pi + 2); b <= pi + 2; ++b) {
+            mbar_wait(&tempty[b], (pbits >> b) & 1u);
+            pbits ^= 1u << b;
+          }
+          tc_fence_after();
+          const uint32_t a_pl = s_lo + slot * slab16;
+          const uint32_t dcol = tmem_base + (uint32_t)pi * NT;
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int kc = 0; kc < KCH; ++kc) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  const uint32_t a_lo = a_pl + (uint32_t)kc * chunk16 + (uint32_t)((((kh * HALO_W + kw) * ROWB) >> 4) + kk * 2);
+                  const uint32_t b_lo = w_lo + (uint32_t)(((kh * 3 + kw) * KCH + kc)) * W_TILE16 + (uint32_t)(kk * 2);
+                  if (leader)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                        "setp.ne.b32 p, %6, 0;\n\t"
+                        "mov.b64 da, {%1, %2};\n\t"
+                        "mov.b64 db, {%3, %4};\n\t"
+                        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+                        ::"r"(dcol), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(B_HI), "r"(IDESC), "r"(1u)
+                        : "memory");
+                }
+              }
+            }
+          }
+          if (leader) {
+            tc_commit_pair(&tfull[pi]);                       // block pi has received its last contribution
+            if (pi == sc.nd + 1) { tc_commit_pair(&tfull[pi + 1]); tc_commit_pair(&tfull[pi + 2]); }
+            tc_commit_pair(&sempty[slot]);
+          }
+          __syncwarp();
+          if (++slot == (uint32_t)p.nslab) { slot = 0; sph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs): drain, store, clear ======================
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int tid128 = ((int)threadIdx.x - 64) & 127;
+    const uint32_t bar_id = 1u + (uint32_t)grp;
+    const int row = q * 32 + lane;
+    const int lw = row % HW_T, lh = row / HW_T;
+    const float slope = p.slope ? __ldg(p.slope) : 0.f;
+    const float neg = act_neg(p.act, slope);
+    const bool clamp0 = p.act == COMA_ACT_LEAKY_RELU, do_stats = p.stats != nullptr;
+    float* gstat = sstat + (size_t)grp * 11 * NT;
+    float* cA = gstat + 8 * NT;
+    float* cS = cA + NT;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lead_tempty = mapa_rank(&tempty[0], 0);
+    auto release = [&](int b) {                // clear block b, then tell the leader's MMA warp it is free
+#pragma unroll
+      for (int c0 = 0; c0 < NT; c0 += 16) tc_st16_zero(lane_base + (uint32_t)(b * NT + c0));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty + (uint32_t)b * 8u);
+    };
+    for (int b = grp; b < kPairBlocks; b += kPairEpi) release(b);
+    uint32_t bcount = 0, ebits = 0;
+    for (int u = pair; u < units; u += npairs) {
+      const SegCoord sc = decode_seg(p, 2 * u + (int)rank);
+      const int oh = sc.h0 + lh, ow = sc.w0 + lw;
+      const bool valid = oh < p.H && ow < p.W;
+      epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)sc.b * p.Cout, n0, NT, cA, cS, tid128, bar_id);
+      float s1[NT], s2[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int b = 0; b < sc.nd + 4; ++b, ++bcount) {
+        if ((bcount % kPairEpi) != (uint32_t)grp) { ebits ^= 1u << b; continue; }
+        mbar_wait(&tfull[b], (ebits >> b) & 1u);
+        ebits ^= 1u << b;
+        tc_fence_after();
+        if (b >= 2 && b < sc.nd + 2) {
+          __nv_bfloat16* yrow = p.y + ((((int64_t)sc.b * p.D + (sc.d0 + b - 2)) * p.H + oh) * p.W + ow) * p.y_cs + n0;
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t raw[16];
+            tc_ld16(lane_base + (uint32_t)(b * NT + c0), raw);
+            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+          }
+        }
+        release(b);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (p.stats) {
+        float* wstat = gstat + (size_t)q * NT * 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float a = warp_sum(s1[j]), b2 = warp_sum(s2[j]);
+          if (lane == 0) { wstat[j * 2] = a; wstat[j * 2 + 1] = b2; }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int i = tid128; i < NT * 2; i += 128) {
+          const float sm = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * kPairEpi + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer may still be reading this CTA's weights / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1824,6 +2076,86 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 }  // namespace
 
+// ---- CTA-pair kernel planning ----
+struct PairPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_bytes; size_t smem; };
+
+static PairPlan plan_pair(const coma_conv_args& a) {
+  PairPlan t{};
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_PAIR"); return e && e[0] == '1'; }();
+  static const bool all64 = [] { const char* e = getenv("COMA_PAIR_CIN64"); return !(e && e[0] == '0'); }();   // Cin = 64 too (1.1-1.3x)
+  if (off || a.transposed || a.ksize != 3 || a.stride != 1 || a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0 || a.in_scale) return t;
+  if (!(a.Cin == 128 || (all64 && a.Cin == 64)) || a.Cout % 32 != 0 || a.Cout / 32 > 4 || a.act == COMA_ACT_SIGMOID) return t;
+  if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return t;
+  if (a.Wo < 2 * HW_T || a.Ho < HH_T) return t;
+  t.cols_w = (a.Wo + HW_T - 1) / HW_T;
+  if (t.cols_w % 2 != 0) return t;                       // the two CTAs of a pair take w-adjacent columns
+  t.cols_h = (a.Ho + HH_T - 1) / HH_T;
+  t.KCH = a.Cin / 64;
+  t.rowb = 128;
+  t.chunk_bytes = ((uint32_t)HALO_ROWS * t.rowb + 1023u) & ~1023u;
+  t.slab_bytes = t.chunk_bytes * (uint32_t)t.KCH;
+  t.w_bytes = 9u * (uint32_t)t.KCH * 48u * t.rowb;       // HALF = 3 * 32 / 2 rows per (tap, chunk)
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kPairBlocks) * 8 + 16 + (size_t)22 * 32 * sizeof(float) + 64;
+  const size_t fixed = 1024 + ((t.w_bytes + 1023u) & ~1023u) + tail;
+  const size_t budget = 222 * 1024;
+  if (fixed + 2 * (size_t)t.slab_bytes > budget) return t;
+  int nslab = (int)((budget - fixed) / t.slab_bytes);
+  t.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
+  t.smem = fixed + (size_t)t.nslab * t.slab_bytes;
+  int segs = (a.Do + kPairMaxND - 1) / kPairMaxND;
+  // enough units (pairs of segments) to give every SM pair a few
+  const int ncols = a.B * t.cols_w * t.cols_h / 2;
+  const int want = (2 * num_sms() + ncols - 1) / ncols;
+  if (segs < want) segs = want;
+  if (segs > a.Do) segs = a.Do;
+  t.DS = (a.Do + segs - 1) / segs;
+  t.segs_d = (a.Do + t.DS - 1) / t.DS;
+  t.ok = true;
+  return t;
+}
+
+template <int KCH>
+static int launch_pair(const coma_conv_args& a, const PairPlan& t, cudaStream_t stream) {
+  constexpr int NT = 32, KC = 64;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wi * a.x_cs * 2, (cuuint64_t)a.Hi * a.Wi * a.x_cs * 2,
+                             (cuuint64_t)a.Di * a.Hi * a.Wi * a.x_cs * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
+    if (!make_map(&tmA, base, 5, dims, strides, box, estr, (int)t.rowb)) return COMA_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)27 * a.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 16};
+    cuuint32_t estr[2] = {1, 1};
+    if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, (int)t.rowb)) return COMA_ERR_CUDA;
+  }
+  HaloParams p{};
+  p.B = a.B; p.D = a.Do; p.H = a.Ho; p.W = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout; p.KC = KC;
+  p.cols_w = t.cols_w; p.cols_h = t.cols_h; p.segs_d = t.segs_d; p.DS = t.DS;
+  p.total_segs = a.B * t.cols_w * t.cols_h * t.segs_d;
+  p.nslab = t.nslab; p.rowb = t.rowb; p.slab_bytes = t.slab_bytes; p.slab_tx = (uint32_t)HALO_ROWS * t.rowb * (uint32_t)KCH;
+  p.chunk_bytes = t.chunk_bytes; p.chunk_tx = (uint32_t)HALO_ROWS * t.rowb;
+  p.w_tile_bytes = 48u * t.rowb; p.w_bytes = t.w_bytes;
+  p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
+  p.stat_chunks = t.cols_w * t.cols_h * t.segs_d * kPairEpi;
+  p.tmem_cols = 512;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(conv_pair_kernel<NT, KC, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  const int nsplit = a.Cout / NT;
+  int npairs = num_sms() / 2 / nsplit;
+  if (npairs < 1) npairs = 1;
+  if (npairs > p.total_segs / 2) npairs = p.total_segs / 2;
+  conv_pair_kernel<NT, KC, KCH><<<dim3((unsigned)(2 * npairs), (unsigned)nsplit), kPairThreads, t.smem, stream>>>(tmA, tmB, p);
+  COMA_CHECK_LAUNCH("conv_pair");
+  return COMA_OK;
+}
+
 // ---- tap-packed kernel (few input channels) ----
 struct TapsPlan { bool ok; int cols_w, cols_h, segs_d, DS; size_t smem; };
 
@@ -1921,6 +2253,10 @@ static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int&
 
 int conv_tc_stat_chunks(const coma_conv_args& a) {
   {
+    const PairPlan pp = plan_pair(a);
+    if (pp.ok) return pp.cols_w * pp.cols_h * pp.segs_d * kPairEpi;
+  }
+  {
     const TapsPlan t = plan_taps(a);
     if (t.ok) return t.cols_w * t.cols_h * t.segs_d * kTapEpi;
   }
@@ -1969,6 +2305,10 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
 }
 
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
+  {
+    const PairPlan pp = plan_pair(a);
+    if (pp.ok) return pp.KCH == 2 ? launch_pair<2>(a, pp, stream) : launch_pair<1>(a, pp, stream);
+  }
   {
     const TapsPlan t = plan_taps(a);
     if (t.ok) return conv_taps_launch(a, t, stream);

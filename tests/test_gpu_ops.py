@@ -367,6 +367,11 @@ TC_CASES = [
     (1, 16, 16, 20, 32, 34, 3, 2, False),    # 32B swizzle, two epilogue warpgroups
     (1, 32, 128, 9, 32, 16, 3, 2, False),    # Cout split 2 x 64
     (3, 32, 32, 40, 64, 32, 3, 2, False),    # many segments per CTA: ring wrap and phase bookkeeping
+    # CTA-pair kernel (cta_group::2, Cin = 128, even number of 8-wide columns)
+    (2, 128, 64, 13, 32, 32, 3, 1, False),   # two Cout splits, several units per pair, two depth segments
+    (1, 128, 32, 27, 17, 16, 3, 1, False),   # ragged h, three depth segments
+    (1, 128, 128, 12, 16, 16, 3, 1, False),  # four Cout splits, a full 12-plane segment
+    (2, 64, 64, 9, 20, 40, 3, 1, False),     # one K chunk, ragged h, odd number of units per pair
     # tap-packed kernel for 1 / 2 / 4 input channels (K = 27 * Cin, A tiles gathered by builder warps)
     (2, 1, 32, 12, 32, 16, 3, 1, False),     # the head conv on the 1-channel MRI
     (1, 2, 16, 9, 17, 12, 3, 1, False),      # ragged tiles, two K chunks (TMA needs W * Cin to be a multiple of 8)
