@@ -1654,8 +1654,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
 // expect_tx), both epilogues arrive on the leader's accumulator-free barriers through shared::cluster addresses, and the
 // leader's tcgen05.commit multicasts "accumulator ready" / "slab free" to both CTAs.
 // ================================================================================================
-constexpr int kPairBlocks = 16, kPairMaxND = kPairBlocks - 4, kPairEpi = 2;
-constexpr int kPairThreads = 64 + 128 * kPairEpi;
+constexpr int kPairBlocks = 16, kPairMaxND = kPairBlocks - 4;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -1688,8 +1687,9 @@ __device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
                ::"r"(taddr), "r"(0u) : "memory");
 }
 
-template <int NT, int KC, int KCH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+// EPI epilogue warpgroups per CTA, CPS CTAs per SM (few channels: more issuing warps and epilogue warps per SM)
+template <int NT, int KC, int KCH, int EPI, int CPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI, CPS)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   constexpr uint32_t ROWB = KC * 2u, HALF = 3u * NT / 2u;                  // weight rows per CTA and (tap, K chunk): half of [kd2|kd1|kd0] x NT
   constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
@@ -1716,18 +1716,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    // this CTA's half of every weight tile: rows [HALF*rank, HALF*rank + HALF) of [kd=2 | kd=1 | kd=0] x NT, in 16-row boxes
+    // this CTA's half of every weight tile: rows [HALF*rank, HALF*rank + HALF) of [kd=2 | kd=1 | kd=0] x NT, in 8-row boxes
     mbar_expect_tx(wfull, p.w_bytes);
     for (int t9 = 0; t9 < 9; ++t9)
       for (int kc = 0; kc < KCH; ++kc)
-        for (uint32_t q = 0; q < HALF / 16u; ++q) {
-          const uint32_t j0 = HALF * rank + 16u * q;
+        for (uint32_t q = 0; q < HALF / 8u; ++q) {
+          const uint32_t j0 = HALF * rank + 8u * q;
           const int kd = 2 - (int)(j0 / NT), co0 = (int)(j0 % NT);
-          tma_load_2d(wreg + (size_t)((t9 * KCH + kc) * HALF + 16u * q) * ROWB, &tmB, wfull, kc * KC, (kd * 9 + t9) * p.Cout + n0 + co0);
+          tma_load_2d(wreg + (size_t)((t9 * KCH + kc) * HALF + 8u * q) * ROWB, &tmB, wfull, kc * KC, (kd * 9 + t9) * p.Cout + n0 + co0);
         }
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kPairBlocks * NT)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -1834,7 +1834,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_tempty + (uint32_t)b * 8u);
     };
-    for (int b = grp; b < kPairBlocks; b += kPairEpi) release(b);
+    for (int b = grp; b < kPairBlocks; b += EPI) release(b);
     uint32_t bcount = 0, ebits = 0;
     for (int u = pair; u < units; u += npairs) {
       const SegCoord sc = decode_seg(p, 2 * u + (int)rank);
@@ -1845,7 +1845,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < NT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
       for (int b = 0; b < sc.nd + 4; ++b, ++bcount) {
-        if ((bcount % kPairEpi) != (uint32_t)grp) { ebits ^= 1u << b; continue; }
+        if (EPI > 1 && (bcount % EPI) != (uint32_t)grp) { ebits ^= 1u << b; continue; }
         mbar_wait(&tfull[b], (ebits >> b) & 1u);
         ebits ^= 1u << b;
         tc_fence_after();
@@ -1871,7 +1871,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         for (int i = tid128; i < NT * 2; i += 128) {
           const float sm = gstat[i] + gstat[NT * 2 + i] + gstat[NT * 4 + i] + gstat[NT * 6 + i];
-          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * kPairEpi + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
+          p.stats[(((int64_t)sc.b * p.stat_chunks + sc.chunk * EPI + grp) * p.Cout + n0 + (i >> 1)) * 2 + (i & 1)] = sm;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
@@ -1883,7 +1883,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();                       // the peer may still be reading this CTA's weights / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kPairBlocks * NT)) : "memory");
   }
 }
 
@@ -2077,27 +2077,36 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 }  // namespace
 
 // ---- CTA-pair kernel planning ----
-struct PairPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, KCH; uint32_t rowb, slab_bytes, chunk_bytes, w_bytes; size_t smem; };
+struct PairPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, KCH, KC, NT, EPI, CPS; uint32_t rowb, slab_bytes, chunk_bytes, w_bytes; size_t smem; };
 
 static PairPlan plan_pair(const coma_conv_args& a) {
   PairPlan t{};
   static const bool off = [] { const char* e = getenv("COMA_DISABLE_PAIR"); return e && e[0] == '1'; }();
   static const bool all64 = [] { const char* e = getenv("COMA_PAIR_CIN64"); return !(e && e[0] == '0'); }();   // Cin = 64 too (1.1-1.3x)
+  static const bool small = [] { const char* e = getenv("COMA_PAIR_SMALL"); return e && e[0] == '1'; }();       // 16 -> 16 (experimental)
   if (off || a.transposed || a.ksize != 3 || a.stride != 1 || a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0 || a.in_scale) return t;
-  if (!(a.Cin == 128 || (all64 && a.Cin == 64)) || a.Cout % 32 != 0 || a.Cout / 32 > 4 || a.act == COMA_ACT_SIGMOID) return t;
+  if (a.act == COMA_ACT_SIGMOID) return t;
+  if (a.Cin == 128 || (all64 && a.Cin == 64)) {
+    if (a.Cout % 32 != 0 || a.Cout / 32 > 4) return t;
+    t.KC = 64; t.NT = 32; t.EPI = 2; t.CPS = 1;
+  } else if (small && a.Cin == 16 && a.Cout == 16) {
+    t.KC = 16; t.NT = 16; t.EPI = 1; t.CPS = 2;
+  } else {
+    return t;
+  }
   if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return t;
   if (a.Wo < 2 * HW_T || a.Ho < HH_T) return t;
   t.cols_w = (a.Wo + HW_T - 1) / HW_T;
   if (t.cols_w % 2 != 0) return t;                       // the two CTAs of a pair take w-adjacent columns
   t.cols_h = (a.Ho + HH_T - 1) / HH_T;
-  t.KCH = a.Cin / 64;
-  t.rowb = 128;
+  t.KCH = a.Cin / t.KC;
+  t.rowb = (uint32_t)t.KC * 2u;
   t.chunk_bytes = ((uint32_t)HALO_ROWS * t.rowb + 1023u) & ~1023u;
   t.slab_bytes = t.chunk_bytes * (uint32_t)t.KCH;
-  t.w_bytes = 9u * (uint32_t)t.KCH * 48u * t.rowb;       // HALF = 3 * 32 / 2 rows per (tap, chunk)
-  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kPairBlocks) * 8 + 16 + (size_t)22 * 32 * sizeof(float) + 64;
+  t.w_bytes = 9u * (uint32_t)t.KCH * (3u * (uint32_t)t.NT / 2u) * t.rowb;       // HALF = 3 * NT / 2 rows per (tap, chunk)
+  const size_t tail = (2 * kMaxSlabs + 1 + 2 * kPairBlocks) * 8 + 16 + (size_t)22 * t.NT * sizeof(float) + 64;
   const size_t fixed = 1024 + ((t.w_bytes + 1023u) & ~1023u) + tail;
-  const size_t budget = 222 * 1024;
+  const size_t budget = (t.CPS == 1 ? 222 : 110) * 1024;
   if (fixed + 2 * (size_t)t.slab_bytes > budget) return t;
   int nslab = (int)((budget - fixed) / t.slab_bytes);
   t.nslab = nslab > kMaxSlabs ? kMaxSlabs : nslab;
@@ -2105,7 +2114,7 @@ static PairPlan plan_pair(const coma_conv_args& a) {
   int segs = (a.Do + kPairMaxND - 1) / kPairMaxND;
   // enough units (pairs of segments) to give every SM pair a few
   const int ncols = a.B * t.cols_w * t.cols_h / 2;
-  const int want = (2 * num_sms() + ncols - 1) / ncols;
+  const int want = (2 * num_sms() * t.CPS + ncols - 1) / ncols;
   if (segs < want) segs = want;
   if (segs > a.Do) segs = a.Do;
   t.DS = (a.Do + segs - 1) / segs;
@@ -2114,9 +2123,8 @@ static PairPlan plan_pair(const coma_conv_args& a) {
   return t;
 }
 
-template <int KCH>
+template <int NT, int KC, int KCH, int EPI, int CPS>
 static int launch_pair(const coma_conv_args& a, const PairPlan& t, cudaStream_t stream) {
-  constexpr int NT = 32, KC = 64;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.Di, (cuuint64_t)a.B};
@@ -2130,7 +2138,7 @@ static int launch_pair(const coma_conv_args& a, const PairPlan& t, cudaStream_t 
   {
     cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)27 * a.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, 16};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 8};
     cuuint32_t estr[2] = {1, 1};
     if (!make_map(&tmB, const_cast<void*>(a.w), 2, dims, strides, box, estr, (int)t.rowb)) return COMA_ERR_CUDA;
   }
@@ -2140,20 +2148,28 @@ static int launch_pair(const coma_conv_args& a, const PairPlan& t, cudaStream_t 
   p.total_segs = a.B * t.cols_w * t.cols_h * t.segs_d;
   p.nslab = t.nslab; p.rowb = t.rowb; p.slab_bytes = t.slab_bytes; p.slab_tx = (uint32_t)HALO_ROWS * t.rowb * (uint32_t)KCH;
   p.chunk_bytes = t.chunk_bytes; p.chunk_tx = (uint32_t)HALO_ROWS * t.rowb;
-  p.w_tile_bytes = 48u * t.rowb; p.w_bytes = t.w_bytes;
+  p.w_tile_bytes = (3u * NT / 2u) * t.rowb; p.w_bytes = t.w_bytes;
   p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
-  p.stat_chunks = t.cols_w * t.cols_h * t.segs_d * kPairEpi;
-  p.tmem_cols = 512;
+  p.stat_chunks = t.cols_w * t.cols_h * t.segs_d * EPI;
+  p.tmem_cols = kPairBlocks * NT;
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(conv_pair_kernel<NT, KC, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(conv_pair_kernel<NT, KC, KCH, EPI, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (CPS == 1 ? 227 : 112) * 1024); attr_set = true; }
   const int nsplit = a.Cout / NT;
-  int npairs = num_sms() / 2 / nsplit;
+  int npairs = num_sms() * CPS / 2 / nsplit;
   if (npairs < 1) npairs = 1;
   if (npairs > p.total_segs / 2) npairs = p.total_segs / 2;
-  conv_pair_kernel<NT, KC, KCH><<<dim3((unsigned)(2 * npairs), (unsigned)nsplit), kPairThreads, t.smem, stream>>>(tmA, tmB, p);
+  conv_pair_kernel<NT, KC, KCH, EPI, CPS><<<dim3((unsigned)(2 * npairs), (unsigned)nsplit), 64 + 128 * EPI, t.smem, stream>>>(tmA, tmB, p);
   COMA_CHECK_LAUNCH("conv_pair");
   return COMA_OK;
+}
+
+static int conv_pair_launch(const coma_conv_args& a, const PairPlan& t, cudaStream_t stream) {
+  if (t.KC == 64 && t.KCH == 2) return launch_pair<32, 64, 2, 2, 1>(a, t, stream);
+  if (t.KC == 64 && t.KCH == 1) return launch_pair<32, 64, 1, 2, 1>(a, t, stream);
+  if (t.KC == 16) return launch_pair<16, 16, 1, 1, 2>(a, t, stream);
+  set_error("conv_pair: unsupported channel combination");
+  return COMA_ERR_UNSUPPORTED;
 }
 
 // ---- tap-packed kernel (few input channels) ----
@@ -2254,7 +2270,7 @@ static void tile_counts(const coma_conv_args& a, int& tw, int& th, int& td, int&
 int conv_tc_stat_chunks(const coma_conv_args& a) {
   {
     const PairPlan pp = plan_pair(a);
-    if (pp.ok) return pp.cols_w * pp.cols_h * pp.segs_d * kPairEpi;
+    if (pp.ok) return pp.cols_w * pp.cols_h * pp.segs_d * pp.EPI;
   }
   {
     const TapsPlan t = plan_taps(a);
@@ -2307,7 +2323,7 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
   {
     const PairPlan pp = plan_pair(a);
-    if (pp.ok) return pp.KCH == 2 ? launch_pair<2>(a, pp, stream) : launch_pair<1>(a, pp, stream);
+    if (pp.ok) return conv_pair_launch(a, pp, stream);
   }
   {
     const TapsPlan t = plan_taps(a);

@@ -11,6 +11,13 @@ namespace coma {
 
 constexpr int kMaxRoi = 64;
 
+// 16 bf16 channels of one voxel, [c0, c1, c2, 0, ...]: one 256-bit store = one full 32-byte sector (sm_100 st.global.v8)
+__device__ __forceinline__ void store16_bf16_head(__nv_bfloat16* o, float c0, float c1, float c2) {
+  const __nv_bfloat162 p01 = __floats2bfloat162_rn(c0, c1), p23 = __floats2bfloat162_rn(c2, 0.f);
+  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&p01), w1 = *reinterpret_cast<const uint32_t*>(&p23);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %3, %3, %3, %3, %3};" ::"l"(o), "r"(w0), "r"(w1), "r"(0u) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) roi_paint_kernel(coma_roi_paint_args a) {
   __shared__ float ids[kMaxRoi];
@@ -33,7 +40,9 @@ __global__ void __launch_bounds__(256) roi_paint_kernel(coma_roi_paint_args a) {
         if (label == ids[i]) { loc = lut[2 * i]; sd = lut[2 * i + 1]; }
     }
     T* o = ob + v * a.out_cs;
-    if ((a.out_cs & 7) == 0) {   // 16-byte vector stores: [prompt, saliency, suvr, 0, ...]
+    if (sizeof(T) == 2 && a.out_cs == 16 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+      store16_bf16_head(reinterpret_cast<__nv_bfloat16*>(o), __ldg(prompt + v), sd, loc);
+    } else if ((a.out_cs & 7) == 0) {   // 16-byte vector stores: [prompt, saliency, suvr, 0, ...]
       float vals[8] = {__ldg(prompt + v), sd, loc, 0.f, 0.f, 0.f, 0.f, 0.f};
       store8(o, vals);
       const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -92,7 +101,9 @@ __global__ void __launch_bounds__(256) pack2_kernel(coma_pack2_args a) {
       const int64_t v = vb + (int64_t)u * gridDim.x * 256;
       if (v >= a.V) continue;
       T* o = d + v * a.dst_cs;
-      if (vec) {
+      if (sizeof(T) == 2 && a.dst_cs == 16 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+        store16_bf16_head(reinterpret_cast<__nv_bfloat16*>(o), va[u], vbv[u], 0.f);
+      } else if (vec) {
         float vals[8] = {va[u], vbv[u], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store8(o, vals);
         const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
