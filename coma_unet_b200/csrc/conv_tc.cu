@@ -165,53 +165,83 @@ __device__ __forceinline__ float4 lds128(const float* p) {
   return v;
 }
 
+// One 16-channel chunk of an accumulator row: v = cA * acc + cS (cS already holds cA * bias + shift), statistics of acc + bias,
+// activation, bf16 pack, one 256-bit store.  The epilogue warps are instruction-issue-bound on the small-channel and transposed
+// kernels, so the common cases skip work per element: `unit` (no scale: cA == 1 and cS == bias, so v doubles as the statistics
+// operand), identity activation (InstanceNorm layers: raw output + statistics), and ReLU as one packed max on the bf16 pairs
+// (relu(round(u)) == round(relu(u))); only PReLU / LeakyReLU take the fp32 min/max/fma path.
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const float* cA, const float* cS, const float* cB, bool valid,
                                             float neg, bool clamp0, float slope, bool stats, float* s1, float* s2,
-                                            __nv_bfloat16* yrow, int c_abs, int y_cn, int y_cs) {
+                                            __nv_bfloat16* yrow, int c_abs, int y_cn, int y_cs, bool unit) {
   float v[16];
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    const float4 a = lds128(cA + 4 * q4), sh = lds128(cS + 4 * q4);
-    v[4 * q4 + 0] = fmaf(a.x, __uint_as_float(raw[4 * q4 + 0]), sh.x);
-    v[4 * q4 + 1] = fmaf(a.y, __uint_as_float(raw[4 * q4 + 1]), sh.y);
-    v[4 * q4 + 2] = fmaf(a.z, __uint_as_float(raw[4 * q4 + 2]), sh.z);
-    v[4 * q4 + 3] = fmaf(a.w, __uint_as_float(raw[4 * q4 + 3]), sh.w);
-  }
-  if (stats) {     // statistics of conv + bias (the input of the following Instance/BatchNorm)
+  if (unit) {
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
-      const float4 bb = lds128(cB + 4 * q4);
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+      const float4 sh = lds128(cS + 4 * q4);
+      v[4 * q4 + 0] = __uint_as_float(raw[4 * q4 + 0]) + sh.x;
+      v[4 * q4 + 1] = __uint_as_float(raw[4 * q4 + 1]) + sh.y;
+      v[4 * q4 + 2] = __uint_as_float(raw[4 * q4 + 2]) + sh.z;
+      v[4 * q4 + 3] = __uint_as_float(raw[4 * q4 + 3]) + sh.w;
+    }
+    if (stats && valid) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float t = valid ? __uint_as_float(raw[4 * q4 + e]) + bv[e] : 0.f;
-        s1[4 * q4 + e] += t;
-        s2[4 * q4 + e] = fmaf(t, t, s2[4 * q4 + e]);
+      for (int j = 0; j < 16; ++j) {
+        s1[j] += v[j];
+        s2[j] = fmaf(v[j], v[j], s2[j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 a = lds128(cA + 4 * q4), sh = lds128(cS + 4 * q4);
+      v[4 * q4 + 0] = fmaf(a.x, __uint_as_float(raw[4 * q4 + 0]), sh.x);
+      v[4 * q4 + 1] = fmaf(a.y, __uint_as_float(raw[4 * q4 + 1]), sh.y);
+      v[4 * q4 + 2] = fmaf(a.z, __uint_as_float(raw[4 * q4 + 2]), sh.z);
+      v[4 * q4 + 3] = fmaf(a.w, __uint_as_float(raw[4 * q4 + 3]), sh.w);
+    }
+    if (stats && valid) {     // statistics of conv + bias (the input of the following Instance/BatchNorm)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 bb = lds128(cB + 4 * q4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float t = __uint_as_float(raw[4 * q4 + e]) + bv[e];
+          s1[4 * q4 + e] += t;
+          s2[4 * q4 + e] = fmaf(t, t, s2[4 * q4 + e]);
+        }
       }
     }
   }
   if (!valid) return;
+  const bool ident = neg == 1.f && !clamp0, relu = neg == 0.f && !clamp0;
+  if (!ident && !relu) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float lo = fminf(v[j], 0.f), hi = fmaxf(v[j], 0.f);
-    v[j] = hi + (clamp0 ? fmaxf(slope * lo, 0.f) : neg * lo);
+    for (int j = 0; j < 16; ++j) {
+      const float lo = fminf(v[j], 0.f), hi = fmaxf(v[j], 0.f);
+      v[j] = hi + (clamp0 ? fmaxf(slope * lo, 0.f) : neg * lo);
+    }
   }
   if (c_abs + 16 <= y_cn && (y_cs & 7) == 0) {
-    uint4 lo, hi;
-    lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-    hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) asm("max.bf16x2 %0, %1, %2;" : "=r"(w[j]) : "r"(w[j]), "r"(0u));
+    }
     if ((reinterpret_cast<uintptr_t>(yrow) & 31) == 0) {
       // one 256-bit store = one full 32-byte sector per voxel (two 128-bit stores cost the LSU two half-sector writes)
       asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                   ::"l"(yrow), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+                   ::"l"(yrow), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
     } else {
-      reinterpret_cast<uint4*>(yrow)[0] = lo;
-      reinterpret_cast<uint4*>(yrow)[1] = hi;
+      reinterpret_cast<uint4*>(yrow)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(yrow)[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (c_abs + j < y_cn) yrow[j] = __float2bfloat16_rn(v[j]);
+      if (c_abs + j < y_cn) yrow[j] = __float2bfloat16_rn(relu ? fmaxf(v[j], 0.f) : v[j]);
   }
 }
 
@@ -398,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float s1c[16], s2c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1c[j] = 0.f; s2c[j] = 0.f; }
-        epi_chunk16(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+        epi_chunk16(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs, p.scale == nullptr);
         if (do_stats) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -636,7 +666,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t raw[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), raw);
-          epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
+          epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs, p.scale == nullptr);
         }
         tc_fence_before();
         __syncwarp();
@@ -776,7 +806,7 @@ __device__ __forceinline__ void ring_epilogue(const HaloParams& p, uint32_t tmem
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t raw[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + blk * NT + (uint32_t)c0, raw);
-        epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+        epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs, p.scale == nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -1230,7 +1260,7 @@ convT_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t raw[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 8 * NT + cls * NT + c0), raw);
-            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs);
+            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, c0, p.y_cn, p.y_cs, p.scale == nullptr);
           }
         }
         tc_fence_before();
@@ -1855,7 +1885,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t raw[16];
             tc_ld16(lane_base + (uint32_t)(b * NT + c0), raw);
-            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs);
+            epi_chunk16(raw, cA + c0, cS + c0, cS + NT + c0, valid, neg, clamp0, slope, do_stats, s1 + c0, s2 + c0, yrow + c0, n0 + c0, p.y_cn, p.y_cs, p.scale == nullptr);
           }
         }
         release(b);
