@@ -77,8 +77,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// three blocks (24 warps) per SM: each warp's load -> smem -> mma -> sigmoid -> store chain is latency-bound, HBM wants them all
 template <int C>
-__global__ void __launch_bounds__(256) gate_mma_kernel(coma_gate_args a) {
+__global__ void __launch_bounds__(256, 3) gate_mma_kernel(coma_gate_args a) {
   constexpr int F = C / 2, LD = C + 8, NTILES = F / 8, CV = C / 8;
   extern __shared__ __align__(16) uint8_t gsm[];
   __nv_bfloat16* swg = reinterpret_cast<__nv_bfloat16*>(gsm);            // [F][LD]
