@@ -256,6 +256,45 @@ __global__ void __launch_bounds__(kPwThreads) conv_pw1_kernel(coma_conv_args a, 
   }
 }
 
+
+// Pointwise conv from ONE input channel (the data gradient of the one-channel heads: dx[v][c] = dy[v] * w[c], per-sample
+// weights for the expert-mixed reduce_channels): an outer product, pure HBM write traffic.  One thread = one voxel x 8 channels.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_pw_from1_kernel(coma_conv_args a) {
+  const int b = blockIdx.y;
+  const int CV = a.Cout >> 3, cvec = threadIdx.x % CV, vlane = threadIdx.x / CV, lanes = 256 / CV;
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride + cvec * 8;      // packed w[tap=0][Cout][Cin=1]
+  float w8[8], s8[8], h8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int co = cvec * 8 + e;
+    const float bias = a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride + co) : 0.f;
+    const float sc = a.scale ? __ldg(a.scale + (int64_t)b * a.Cout + co) : 1.f;
+    w8[e] = Elem<T>::ld(wb + e) * sc;
+    h8[e] = fmaf(sc, bias, a.scale ? __ldg(a.shift + (int64_t)b * a.Cout + co) : 0.f);
+    s8[e] = 0.f;
+  }
+  (void)s8;
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co;
+  T* yb = static_cast<T*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co + cvec * 8;
+  for (int64_t v = (int64_t)blockIdx.x * lanes + vlane; v < Vo; v += (int64_t)gridDim.x * lanes) {
+    const float xv = Elem<T>::ld(xb + v * a.x_cs);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = act_fwd(a.act, fmaf(xv, w8[e], h8[e]), slope);
+    store8(yb + v * a.y_cs, o);
+  }
+}
+
+static bool pw_from1_applicable(const coma_conv_args& a) {
+  const int esz = a.dtype == COMA_BF16 ? 2 : 4;
+  return a.ksize == 1 && a.stride == 1 && !a.transposed && a.Cin == 1 && a.Cout % 8 == 0 && a.Cout <= 512 && 256 % (a.Cout / 8) == 0 &&
+         a.y_cn == a.Cout && !a.stats && !a.in_scale && a.y_cs % 8 == 0 && a.y_co % 8 == 0 &&
+         reinterpret_cast<uintptr_t>(a.y) % (8 * esz > 16 ? 16 : 8 * esz) == 0;
+}
+
 static bool pw1_applicable(const coma_conv_args& a) {
   return a.ksize == 1 && a.stride == 1 && !a.transposed && a.Cout == 1 && a.y_cn >= 1 &&
          (a.Cin == 1 || a.Cin == 2 || a.Cin == 3 || a.Cin == 8 || a.Cin == 16 || a.Cin == 32 || a.Cin == 64);
@@ -288,6 +327,16 @@ bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a
 int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : simt_chunks(a); }
 
 int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
+  if (pw_from1_applicable(a)) {
+    const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+    const int lanes = 256 / (a.Cout / 8);
+    const int64_t want = (Vo + lanes * 4 - 1) / (lanes * 4), cap = std::max<int64_t>(1, (int64_t)num_sms() * 8 / a.B);
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min(want, cap)), (unsigned)a.B);
+    if (a.dtype == COMA_BF16) conv_pw_from1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+    else conv_pw_from1_kernel<float><<<grid, 256, 0, stream>>>(a);
+    COMA_CHECK_LAUNCH("conv_pw_from1");
+    return COMA_OK;
+  }
   if (pw1_applicable(a)) return a.dtype == COMA_BF16 ? launch_pw1_t<__nv_bfloat16>(a, stream) : launch_pw1_t<float>(a, stream);
   if (a.dtype == COMA_BF16) return launch_simt_t<__nv_bfloat16>(a, stream);
   return launch_simt_t<float>(a, stream);
