@@ -125,16 +125,24 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(coma_wgrad_args a, int64
 // block of x in shared memory ONCE (cp.async, double buffered) and accumulates all 27 taps from it, one
 // [CgT x CxT] accumulator per tap held in registers across the whole persistent loop (27 x 4 registers per thread).
 // ------------------------------------------------------------------------------------------------
-constexpr int VW = 8, VH = 8, VD = 4, VOX = VW * VH * VD;                 // 256 output voxels per block step
-constexpr int XW = VW + 2, XH = VH + 2, XD = VD + 2, XROWS = XW * XH * XD;  // 600 halo voxels
+// S = conv stride: stride 1 stages 8x8x4 output voxels + a 10x10x6 halo; stride 2 (x index = 2 o + k - 1) stages 8x4x2 output
+// voxels + the 17x9x5 input voxels they touch, and the B fragments step two halo rows per voxel
+template <int S>
+struct HaloGeo {
+  static constexpr int VW = 8, VH = S == 1 ? 8 : 4, VD = S == 1 ? 4 : 2, VOX = VW * VH * VD;
+  static constexpr int E = S == 1 ? 2 : 1;
+  static constexpr int XW = S * VW + E, XH = S * VH + E, XD = S * VD + E, XROWS = XW * XH * XD;
+};
 
 __device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
 }
 
-template <int CGT, int CXT>
+template <int CGT, int CXT, int S>
 __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, int cx_tiles, int nbw, int nbh, int nbd) {
+  using G = HaloGeo<S>;
+  constexpr int VW = G::VW, VH = G::VH, VD = G::VD, VOX = G::VOX, XW = G::XW, XH = G::XH, XROWS = G::XROWS;
   constexpr int LDG = CGT + 8, LDX = CXT + 8;
   constexpr int MT = CGT / 16, NTL = CXT / 8, T = MT * NTL, WT_ = 8 / T;   // tiles, warps per tile (k split)
   static_assert(T <= 8 && 8 % T == 0, "tile layout");
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, i
     }
     for (int i = threadIdx.x; i < XROWS * XV; i += 256) {
       const int row = i / XV, vec = (i % XV) * 8;
-      const int w = w0 - 1 + (row % XW), h = h0 - 1 + (row / XW) % XH, d = d0 - 1 + row / (XW * XH);
+      const int w = S * w0 - 1 + (row % XW), h = S * h0 - 1 + (row / XW) % XH, d = S * d0 - 1 + row / (XW * XH);
       const bool ok = w >= 0 && w < a.Wx && h >= 0 && h < a.Hx && d >= 0 && d < a.Dx;
       const __nv_bfloat16* src = ok ? xp + (((b * a.Dx + d) * a.Hx + h) * a.Wx + w) * a.x_cs + vec : xp;
       cp_async16(sx[buf] + row * LDX + vec, src, ok);
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, i
         const int mat = lane >> 3, r = lane & 7;
         ldsm_x4_t(af, g_s + ((d * VH + 2 * hp) * VW + (mat >> 1) * 8 + r) * LDG + m0 + (mat & 1) * 8);
       }
-      const int lrow = ((lane >> 3) & 1) * XW + (lane & 7);      // second 8 voxels are the next h-line: +XW halo rows
+      const int lrow = ((lane >> 3) & 1) * (S * XW) + (lane & 7) * S;      // second 8 voxels are the next h-line: + S * XW halo rows
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, i
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             uint32_t bf[2];
-            ldsm_x2_t(bf, x_s + (((d + kd) * XH + 2 * hp + kh) * XW + kw + lrow) * LDX + n0);
+            ldsm_x2_t(bf, x_s + (((S * d + kd) * XH + S * 2 * hp + kh) * XW + kw + lrow) * LDX + n0);
             mma_bf16(acc[(kd * 3 + kh) * 3 + kw], af, bf[0], bf[1]);
           }
     }
@@ -231,12 +239,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, i
     }
 }
 
-template <int CGT, int CXT>
+template <int CGT, int CXT, int S = 1>
 int launch_wgrad_halo(const coma_wgrad_args& a, cudaStream_t stream) {
+  using G = HaloGeo<S>;
+  constexpr int VW = G::VW, VH = G::VH, VD = G::VD, VOX = G::VOX, XROWS = G::XROWS;
   constexpr int LDG = CGT + 8, LDX = CXT + 8;
   const size_t smem = (size_t)2 * (VOX * LDG + XROWS * LDX) * sizeof(__nv_bfloat16);
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(wgrad_halo_kernel<CGT, CXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(wgrad_halo_kernel<CGT, CXT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   const int nbw = (a.Wg + VW - 1) / VW, nbh = (a.Hg + VH - 1) / VH, nbd = (a.Dg + VD - 1) / VD;
   const int nblocks = a.B * nbw * nbh * nbd;
   const int cg_tiles = a.Cg / CGT, cx_tiles = a.Cx / CXT;
@@ -244,7 +254,7 @@ int launch_wgrad_halo(const coma_wgrad_args& a, cudaStream_t stream) {
   if (gx < 1) gx = 1;
   if (gx > nblocks) gx = nblocks;
   dim3 grid((unsigned)gx, (unsigned)(cg_tiles * cx_tiles));
-  wgrad_halo_kernel<CGT, CXT><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
+  wgrad_halo_kernel<CGT, CXT, S><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
   COMA_CHECK_LAUNCH("wgrad_halo");
   return COMA_OK;
 }
@@ -264,6 +274,15 @@ int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream) {
     if (g32) return launch_wgrad_halo<32, 16>(a, stream);
     if (x32) return launch_wgrad_halo<16, 32>(a, stream);
     return launch_wgrad_halo<16, 16>(a, stream);
+  }
+  if (!halo_off && a.ksize == 3 && a.stride == 2 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && a.Cg <= 512 && a.Cx <= 512 &&
+      (int64_t)a.Dg * a.Hg * a.Wg >= 8 * 8 * 8) {
+    // strided layers (down-sampling convs and, with the roles of x and dy swapped, the transposed convs)
+    const bool g32 = a.Cg % 32 == 0, x32 = a.Cx % 32 == 0;
+    if (g32 && x32) return launch_wgrad_halo<32, 32, 2>(a, stream);
+    if (g32) return launch_wgrad_halo<32, 16, 2>(a, stream);
+    if (x32) return launch_wgrad_halo<16, 32, 2>(a, stream);
+    return launch_wgrad_halo<16, 16, 2>(a, stream);
   }
   const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
   const int taps = a.ksize * a.ksize * a.ksize;

@@ -62,6 +62,11 @@ CONV_CASES = [
     (1, 64, 32, 16, 16, 16, 3, 1, False),
     (1, 16, 16, 12, 24, 16, 3, 1, False),
     (1, 64, 128, 16, 16, 16, 3, 1, False),  # halo wgrad tiled over 2 x 4 channel tiles
+    # stride-2 halo weight gradient (down-sampling convs; transposed convs with x / dy swapped)
+    (1, 32, 32, 16, 16, 16, 3, 2, False),
+    (1, 16, 32, 18, 20, 22, 3, 2, False),   # ragged blocks in every dim
+    (1, 32, 16, 8, 8, 8, 3, 2, True),
+    (2, 64, 32, 9, 10, 12, 3, 2, True),
 ]
 
 
