@@ -5,6 +5,7 @@ criterions.py:124-211,485-644): import the classes from here instead of the refe
 Requires the in-tree CUDA library (coma_unet_b200/csrc/libcoma_b200.so); there is no CPU fallback.
 """
 from . import _lib
+from . import metrics
 from .criterions import GenerativeContrastiveLoss, RnCLoss, RoiMSE
 from .data import DevicePrefetcher, HostSink, SyntheticVolumeDataset
 from .model import (AttentionLayer, ContrastiveAttentionUNET_DP, ObservableAttentionBlock, ObservableAttentionUnet,
@@ -14,4 +15,4 @@ from .train import train_dp
 
 __all__ = ["ContrastiveAttentionUNET_DP", "ObservableAttentionUnet", "AttentionLayer", "ObservableAttentionBlock",
            "UpBlock", "ProjectionHead", "StackedFusionConvLayers", "RoiMSE", "RnCLoss", "GenerativeContrastiveLoss",
-           "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "_lib"]
+           "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "metrics", "_lib"]

@@ -31,6 +31,11 @@ class ConvArgs(C.Structure):
                 ("in_scale", _vp), ("in_shift", _vp), ("in_slope", _vp), ("in_act", _i32), ("reserved0", _i32)]
 
 
+class EvalMetricsArgs(C.Structure):
+    _fields_ = [("pred", _vp), ("tau", _vp), ("roi", _vp), ("roi_ids", _vp), ("n_roi", _i32), ("B", _i32), ("V", _i64),
+                ("out", _vp)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("g", _vp), ("x", _vp), ("dw", _vp),
                 ("B", _i32), ("Dg", _i32), ("Hg", _i32), ("Wg", _i32), ("Dx", _i32), ("Hx", _i32), ("Wx", _i32),
@@ -124,6 +129,7 @@ EXPORTS = {
     "coma_roi_mse_chunks": (C.c_int, [_i64]),
     "coma_roi_mse_fwd": (C.c_int, [C.POINTER(RoiMseArgs), _vp]),
     "coma_roi_mse_bwd": (C.c_int, [C.POINTER(RoiMseArgs), _vp]),
+    "coma_eval_metrics": (C.c_int, [C.POINTER(EvalMetricsArgs), _vp]),
 }
 
 _lib = None

@@ -276,3 +276,63 @@ extern "C" int coma_roi_mse_bwd(const coma_roi_mse_args* a, coma_stream_t stream
   COMA_CHECK_LAUNCH("roi_mse_bwd");
   return COMA_OK;
 }
+
+// ---- fused evaluation metrics (include/coma_b200.h) ------------------------------------------------------------------
+constexpr int kEvalLut = 4096, kEvalQ = 8;
+
+__global__ void __launch_bounds__(256) eval_metrics_kernel(coma_eval_metrics_args a) {
+  __shared__ int8_t lut[kEvalLut];                    // label value -> ROI slot (-1: not a listed ROI)
+  __shared__ double acc[(kMaxRoi + 1) * kEvalQ];
+  const int b = blockIdx.y, R = a.n_roi;
+  for (int i = threadIdx.x; i < kEvalLut; i += 256) lut[i] = -1;
+  for (int i = threadIdx.x; i < (R + 1) * kEvalQ; i += 256) acc[i] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < R; i += 256) {
+    const int id = a.roi_ids[i];
+    if (id >= 0 && id < kEvalLut) lut[id] = (int8_t)i;
+  }
+  __syncthreads();
+  const float* pp = a.pred + (int64_t)b * a.V;
+  const float* tp = a.tau + (int64_t)b * a.V;
+  const float* rp = a.roi + (int64_t)b * a.V;
+  float g_ad = 0.f, g_d2 = 0.f, g_t = 0.f, g_t2 = 0.f, g_r = 0.f, g_nan = 0.f, g_m = 0.f, g_n = 0.f;
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.V; v += (int64_t)gridDim.x * 256) {
+    const float p = __ldg(pp + v), t = __ldg(tp + v), lab = __ldg(rp + v);
+    const float d = p - t, ad = fabsf(d), d2 = d * d, ratio = fabsf(d / t);
+    const bool isn = ratio != ratio;
+    g_n += 1.f; g_ad += ad; g_d2 += d2; g_t += t; g_t2 = fmaf(t, t, g_t2);
+    if (isn) g_nan += 1.f; else g_r += ratio;
+    if (fabsf(t) > 1e-8f) g_m += 100.f * ratio;
+    const int li = (int)lab;
+    if (lab >= 0.f && lab < (float)kEvalLut && (float)li == lab) {
+      const int slot = lut[li];
+      if (slot >= 0) {
+        double* s = acc + slot * kEvalQ;
+        atomicAdd(s + 0, 1.0); atomicAdd(s + 1, (double)ad); atomicAdd(s + 2, (double)d2); atomicAdd(s + 3, (double)t);
+        atomicAdd(s + 4, (double)t * t);
+        if (isn) atomicAdd(s + 6, 1.0); else atomicAdd(s + 5, (double)ratio);
+      }
+    }
+  }
+  // all-voxel slot: registers -> warp -> shared
+  const float gq[kEvalQ] = {g_n, g_ad, g_d2, g_t, g_t2, g_r, g_nan, g_m};
+#pragma unroll
+  for (int q = 0; q < kEvalQ; ++q) {
+    const float w = warp_sum(gq[q]);
+    if ((threadIdx.x & 31) == 0 && w != 0.f) atomicAdd(acc + R * kEvalQ + q, (double)w);
+  }
+  __syncthreads();
+  double* ob = a.out + (int64_t)b * (R + 1) * kEvalQ;
+  for (int i = threadIdx.x; i < (R + 1) * kEvalQ; i += 256)
+    if (acc[i] != 0.0) atomicAdd(ob + i, acc[i]);
+}
+
+extern "C" int coma_eval_metrics(const coma_eval_metrics_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && a->pred && a->tau && a->roi && a->roi_ids && a->out && a->B > 0 && a->V > 0, "coma_eval_metrics: bad arguments");
+  COMA_CHECK_ARG(a->n_roi >= 0 && a->n_roi <= kMaxRoi, "coma_eval_metrics: at most %d ROIs", kMaxRoi);
+  const int64_t want = (a->V + 256 * 16 - 1) / (256 * 16), cap = std::max<int64_t>(1, (int64_t)num_sms() * 4 / a->B);
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min(want, cap)), (unsigned)a->B);
+  eval_metrics_kernel<<<grid, 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("eval_metrics");
+  return COMA_OK;
+}

@@ -257,6 +257,27 @@ int coma_roi_mse_chunks(int64_t V);
 int coma_roi_mse_fwd(const coma_roi_mse_args* a, coma_stream_t stream);
 int coma_roi_mse_bwd(const coma_roi_mse_args* a, coma_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused evaluation metrics: the step right after inference.  Replaces the batch metric lines
+ * attn_unet_data_parallel.py:1214-1231 and calc_roi_metrics :1361-1397 (36 ROIs x ~10 masked full-volume kernels) by ONE
+ * pass over pred / tau / roi.  Per sample and per slot (n_roi ROI slots in roi_ids order + one all-voxel slot, index n_roi)
+ * eight fp64 sums are ACCUMULATED into `out` (the caller zeroes it), with d = pred - tau:
+ *   [0] voxels  [1] sum |d|  [2] sum d^2  [3] sum tau  [4] sum tau^2
+ *   [5] sum |d / tau| over the non-NaN ratios (an infinite ratio stays in the sum, like torch.nansum)  [6] NaN ratios (0/0)
+ *   [7] sum 100 |d / tau| over |tau| > 1e-8
+ * roi holds FreeSurfer label values as floats; labels must be integers in [0, 4096).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* pred;      /* [B, V] fp32 */
+  const float* tau;       /* [B, V] fp32 */
+  const float* roi;       /* [B, V] fp32 label values */
+  const int32_t* roi_ids; /* [n_roi] device */
+  int32_t n_roi, B;
+  int64_t V;
+  double* out;            /* [B, n_roi + 1, 8] fp64, accumulated into */
+} coma_eval_metrics_args;
+int coma_eval_metrics(const coma_eval_metrics_args* a, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,3 +234,39 @@ def test_non_cubic_volume_matches_oracle():
             got = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi).cpu().numpy()
         assert got.shape == want.shape == (3, 1, 48, 64, 32)
         assert check.scaled_err(got, want) < tol, (dtype, check.scaled_err(got, want))
+
+
+@pytest.mark.parametrize("name", ["m32", "m48"])
+def test_fused_eval_metrics_match_reference_golden(name):
+    """coma_eval_metrics (one pass) against the values the reference's own calc_roi_metrics and metric lines produced."""
+    import os
+    import numpy as np
+    from tests.golden import make_metrics_golden
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.npz"))
+    batch, d, h, w, seed = (int(v) for v in gold[f"{name}/cfg"])
+    pred, tau, roi = (t.to(DEV) for t in make_metrics_golden.case(batch, (d, h, w), seed))
+    sums = cu.metrics.fused_sums(pred, tau, roi, common.ROI_INDICES)
+    vol = [float(v) for v in cu.metrics.volume_metrics(pred, tau, sums=sums)]
+    np.testing.assert_allclose(vol, gold[f"{name}/volume"], rtol=2e-5)
+    z = [torch.zeros(36, device=DEV) for _ in range(5)]
+    got = cu.metrics.calc_roi_metrics(common.ROI_INDICES, None, *z, tau, roi, pred, pred - tau, None)
+    for key, t in zip(("roi_maes", "roi_mapes", "roi_rses", "roi_wrrmses", "roi_nonnan"), got):
+        np.testing.assert_allclose(t.double().cpu().numpy(), gold[f"{name}/{key}"], rtol=5e-5, equal_nan=True, err_msg=key)
+
+
+def test_fused_eval_metrics_full_size_against_oracle():
+    """Batch 8 x 128^3: the fused pass against the oracle's 36 masked passes run on the same device."""
+    from oracle import metrics as ometrics
+    mri, tau, roi, covars, dicts = common.synthetic_batch(8, (128, 128, 128), 51)
+    g = torch.Generator().manual_seed(52)
+    pred = ((tau + 0.2 * torch.randn(tau.shape, generator=g)).clamp_min(0) * (mri > 0)).to(DEV)
+    tau, roi = tau.to(DEV), roi.to(DEV)
+    sums = cu.metrics.fused_sums(pred, tau, roi, common.ROI_INDICES)
+    got_v = cu.metrics.volume_metrics(pred, tau, sums=sums)
+    want_v = ometrics.volume_metrics(pred, tau)
+    for a, b in zip(got_v, want_v):
+        assert abs(float(a) - float(b)) <= 2e-4 * abs(float(b))
+    got = cu.metrics.calc_roi_metrics(common.ROI_INDICES, None, None, None, None, None, None, tau, roi, pred, sums=sums)
+    want = ometrics.calc_roi_metrics(common.ROI_INDICES, tau, roi, pred)
+    for a, b in zip(got, want):
+        torch.testing.assert_close(a.cpu(), b.cpu().float(), rtol=2e-4, atol=0, equal_nan=True)

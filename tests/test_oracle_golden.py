@@ -1,5 +1,7 @@
 """CPU: the oracle restatement against fixtures produced by the reference's own code
 (tests/golden/make_golden.py).  fp32 vs fp32, so the tolerance is the TF32/fp32 bound 1e-4."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -95,3 +97,20 @@ def test_criterions_match_reference():
     rm = ocrit.RoiMSE(torch.tensor([225.0] * 36), common.ROI_INDICES, voxel_wise=False)
     assert check.rel_err([float(rm(pred.detach(), tau, roi))], DATA["crit/roimse_mean"]) < 1e-5
     assert ocrit.RnCLoss()(feats[:1].detach(), covars[:1, -1].float()) == 0.0 and float(DATA["crit/rnc1"][0]) == 0.0
+
+
+def test_metrics_oracle_matches_reference_golden():
+    """oracle/metrics.py against the values the reference's own calc_roi_metrics / metric lines produced
+    (tests/golden/make_metrics_golden.py)."""
+    import numpy as np
+    from oracle import metrics as ometrics
+    from tests.golden import make_metrics_golden
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.npz"))
+    for name in ("m32", "m48"):
+        batch, d, h, w, seed = (int(v) for v in gold[f"{name}/cfg"])
+        pred, tau, roi = make_metrics_golden.case(batch, (d, h, w), seed)
+        vol = [float(v) for v in ometrics.volume_metrics(pred, tau)]
+        np.testing.assert_allclose(vol, gold[f"{name}/volume"], rtol=1e-5)
+        got = ometrics.calc_roi_metrics(common.ROI_INDICES, tau, roi, pred)
+        for key, t in zip(("roi_maes", "roi_mapes", "roi_rses", "roi_wrrmses", "roi_nonnan"), got):
+            np.testing.assert_allclose(t.double().numpy(), gold[f"{name}/{key}"], rtol=1e-5, equal_nan=True)
