@@ -49,11 +49,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -63,7 +70,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -76,7 +83,14 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        # samples taken while the timed region ran; a region shorter than the sampling period borrows the samples of the
+        # warm-up steps right before it (the sampler starts with the warm-up, same load)
+        inside = [l for t, l in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside = [l for t, l in self.lines if self.t0 is None or t <= (self.t1 or t) + 0.05][-4:]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        for line in inside:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -91,7 +105,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_batch(batch, seed, device=None, pin=False):
@@ -326,17 +340,21 @@ def run_ours(args):
             with torch.no_grad():
                 return model(m, c, roi_pred_dicts=dicts, sample_roi_mask=r)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier(world)
-    l0 = _lib.launches
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:           # sampling starts with the warm-up (same load) and is windowed to the timed region
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier(world)
+        torch.cuda.synchronize()
+        l0 = _lib.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.mark_start()
         e0.record()
         for _ in range(args.steps):
             out = step()
         e1.record()
         barrier(world)
+        torch.cuda.synchronize()
+        clocks.mark_end()
         ms = max_over_ranks(e0.elapsed_time(e1), world, device)
     launches = _lib.launches - l0
     value = world * batch * args.steps / (ms / 1000.0)
@@ -446,7 +464,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
