@@ -532,3 +532,20 @@ def test_full_size_stride2_and_transposed_round_trip_shapes_and_adjointness():
     lhs = float((y.float() * g.float()).sum())
     rhs = float((x.float() * xt.float()).sum())
     assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0) + 2e-3 * float(y.float().norm() * g.float().norm()) * 1e-2
+
+
+@pytest.mark.parametrize("case", [(8, 128, 64, 64, 3, 1, False), (8, 64, 32, 128, 3, 1, False), (8, 16, 16, 128, 3, 1, False),
+                                  (8, 32, 64, 128, 3, 2, False), (8, 64, 32, 64, 3, 2, True)])
+def test_warp_specialised_convs_are_run_to_run_identical(case):
+    """A missed barrier or phase slip in the producer / MMA / epilogue pipelines (CTA pair, plane ring, stride 2, transposed)
+    shows up as run-to-run differences: outputs and fused statistics must be bit-identical over repeated launches at the
+    benchmark size."""
+    B, Cin, Cout, D, k, s, tr = case
+    x = rnd(B, D, D, D, Cin, seed=80).bfloat16()
+    wshape = (Cin, Cout, k, k, k) if tr else (Cout, Cin, k, k, k)
+    wp = ops.pack_weight(rnd(*wshape, seed=81, scale=(Cin * 27) ** -0.5), tr, Cin, Cout, torch.bfloat16)
+    y0, s0 = ops.conv_raw(x, wp, None, ksize=k, stride=s, transposed=tr, want_stats=True)
+    y0, s0 = y0.clone(), s0.sum(dim=1).clone()
+    for _ in range(12):
+        y, st = ops.conv_raw(x, wp, None, ksize=k, stride=s, transposed=tr, want_stats=True)
+        assert torch.equal(y, y0) and torch.equal(st.sum(dim=1), s0)
