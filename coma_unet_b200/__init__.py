@@ -7,7 +7,7 @@ Requires the in-tree CUDA library (coma_unet_b200/csrc/libcoma_b200.so); there i
 from . import _lib
 from . import metrics
 from .criterions import GenerativeContrastiveLoss, RnCLoss, RoiMSE
-from .data import DevicePrefetcher, HostSink, SyntheticVolumeDataset
+from .data import DevicePrefetcher, HostSink, SyntheticVolumeDataset, prepare_geometry, prepare_volumes
 from .model import (AttentionLayer, ContrastiveAttentionUNET_DP, ObservableAttentionBlock, ObservableAttentionUnet,
                     ProjectionHead, StackedFusionConvLayers, UpBlock)
 from .parallel import DataParallelEngine
@@ -15,4 +15,5 @@ from .train import train_dp
 
 __all__ = ["ContrastiveAttentionUNET_DP", "ObservableAttentionUnet", "AttentionLayer", "ObservableAttentionBlock",
            "UpBlock", "ProjectionHead", "StackedFusionConvLayers", "RoiMSE", "RnCLoss", "GenerativeContrastiveLoss",
-           "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "metrics", "_lib"]
+           "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "metrics", "_lib",
+           "prepare_geometry", "prepare_volumes"]

@@ -36,6 +36,12 @@ class EvalMetricsArgs(C.Structure):
                 ("out", _vp)]
 
 
+class PrepareArgs(C.Structure):
+    _fields_ = [("mri", _vp), ("tau", _vp), ("roi", _vp), ("mri_out", _vp), ("tau_out", _vp), ("roi_out", _vp),
+                ("in_size", _i32 * 3), ("res_size", _i32 * 3), ("out_size", _i32 * 3), ("pad_before", _i32 * 3),
+                ("ratio", C.c_double * 3), ("default_value", C.c_float)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("g", _vp), ("x", _vp), ("dw", _vp),
                 ("B", _i32), ("Dg", _i32), ("Hg", _i32), ("Wg", _i32), ("Dx", _i32), ("Hx", _i32), ("Wx", _i32),
@@ -130,6 +136,7 @@ EXPORTS = {
     "coma_roi_mse_fwd": (C.c_int, [C.POINTER(RoiMseArgs), _vp]),
     "coma_roi_mse_bwd": (C.c_int, [C.POINTER(RoiMseArgs), _vp]),
     "coma_eval_metrics": (C.c_int, [C.POINTER(EvalMetricsArgs), _vp]),
+    "coma_prepare_volumes": (C.c_int, [C.POINTER(PrepareArgs), _vp]),
 }
 
 _lib = None

@@ -336,3 +336,53 @@ extern "C" int coma_eval_metrics(const coma_eval_metrics_args* a, coma_stream_t 
   COMA_CHECK_LAUNCH("eval_metrics");
   return COMA_OK;
 }
+
+// ---- GPU-side input preparation (include/coma_b200.h) -------------------------------------------------------------------
+__device__ __forceinline__ float nan_to_num(float v) {     // torch.nan_to_num defaults
+  if (v != v) return 0.f;
+  if (v == __int_as_float(0x7f800000)) return 3.402823466e+38f;
+  if (v == __int_as_float(0xff800000)) return -3.402823466e+38f;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) prepare_volumes_kernel(coma_prepare_args a) {
+  const int64_t total = (int64_t)a.out_size[0] * a.out_size[1] * a.out_size[2];
+  for (int64_t o = (int64_t)blockIdx.x * 256 + threadIdx.x; o < total; o += (int64_t)gridDim.x * 256) {
+    const int ox = (int)(o % a.out_size[2]), t = (int)(o / a.out_size[2]);
+    const int oc[3] = {t / a.out_size[1], t % a.out_size[1], ox};
+    bool padded = false, inside = true;
+    int64_t src = 0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const int r = oc[ax] - a.pad_before[ax];
+      if (r < 0 || r >= a.res_size[ax]) padded = true;
+      const double c = (double)r * a.ratio[ax];             // ITK maps indices through physical space in double
+      if (!(c >= -0.5 && c < (double)a.in_size[ax] - 0.5)) inside = false;
+      int n = (int)floor(c + 0.5);
+      n = n < 0 ? 0 : (n >= a.in_size[ax] ? a.in_size[ax] - 1 : n);
+      src = src * a.in_size[ax] + n;
+    }
+    float m = 0.f, tv = 0.f, rv = 0.f;
+    if (!padded) {
+      if (a.mri) m = nan_to_num(inside ? __ldg(a.mri + src) : a.default_value);
+      if (a.tau) tv = nan_to_num(inside ? __ldg(a.tau + src) : a.default_value);
+      if (a.roi) rv = nan_to_num(inside ? __ldg(a.roi + src) : a.default_value);
+    }
+    if (a.mri && a.roi && rv == 0.f) m = 0.f;              // mri[roi == 0] = 0
+    if (a.mri_out) a.mri_out[o] = m;
+    if (a.tau_out) a.tau_out[o] = tv;
+    if (a.roi_out) a.roi_out[o] = rv;
+  }
+}
+
+extern "C" int coma_prepare_volumes(const coma_prepare_args* a, coma_stream_t stream) {
+  COMA_CHECK_ARG(a && (a->mri || a->tau || a->roi), "coma_prepare_volumes: no input");
+  COMA_CHECK_ARG((!a->mri || a->mri_out) && (!a->tau || a->tau_out) && (!a->roi || a->roi_out), "coma_prepare_volumes: missing output");
+  for (int ax = 0; ax < 3; ++ax)
+    COMA_CHECK_ARG(a->in_size[ax] > 0 && a->res_size[ax] > 0 && a->out_size[ax] > 0 && a->pad_before[ax] >= 0 && a->ratio[ax] > 0.0,
+                   "coma_prepare_volumes: bad geometry on axis %d", ax);
+  const int64_t total = (int64_t)a->out_size[0] * a->out_size[1] * a->out_size[2];
+  prepare_volumes_kernel<<<sweep_blocks(total), 256, 0, stream>>>(*a);
+  COMA_CHECK_LAUNCH("prepare_volumes");
+  return COMA_OK;
+}

@@ -10,9 +10,13 @@ what tests and bench.py feed the model.
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from . import _lib
 from .model import ROI_INDICES, ROI_NAMES
 
 
@@ -146,3 +150,65 @@ class HostSink:
         for ev in self.done:
             if ev is not None:
                 ev.synchronize()
+
+
+def prepare_geometry(in_shape, spacing, resize=True, new_spacing=(2.0, 2.0, 2.0), pad_dims=(128, 128, 128)):
+    """Index geometry of the reference's per-sample preparation, per array axis (z, y, x) -- host integers only.
+
+    ``in_shape`` is the [z, y, x] array shape, ``spacing``/``new_spacing`` are (x, y, z) as SimpleITK reports them.  Follows
+    ``resize_volume`` (VolumeDataset.py:241-245: ``int(np.round(size * spacing / new_spacing))``), ``apply_transforms``
+    (:261-264: pad only when the z extent differs from ``pad_dims[-3]``) and ``data_util.pad_volume`` (data_util.py:814-828:
+    ``target_size[i]`` belongs to array axis ``-1 - i``, centred padding, only the y axis is ever cropped, at its end).
+    Returns ``(res_size, out_size, pad_before, ratio)``.
+    """
+    res, ratio = [], []
+    for ax in range(3):
+        j = 2 - ax
+        if resize:
+            res.append(int(np.round(in_shape[ax] * (spacing[j] / new_spacing[j]))))
+            ratio.append(float(new_spacing[j]) / float(spacing[j]))
+        else:
+            res.append(int(in_shape[ax]))
+            ratio.append(1.0)
+    out, before = list(res), [0, 0, 0]
+    if pad_dims is not None and res[0] != pad_dims[-3]:
+        for ax in range(3):
+            target = pad_dims[2 - ax]
+            before[ax] = max(0, (target - res[ax]) // 2)
+            out[ax] = res[ax] + before[ax] + max(0, target - res[ax] - before[ax])
+        if out[1] != pad_dims[1]:
+            out[1] = min(out[1], pad_dims[1])
+    return res, out, before, ratio
+
+
+def prepare_volumes(mri=None, tau=None, roi=None, spacing=(1.0, 1.0, 1.0), resize=True, pad_dims=(128, 128, 128),
+                    default_value=8.0):
+    """GPU replacement for what the reference datasets do to one sample between the file read and the model (SURVEY 8f
+    rank 4): ``load_volume_file`` for each of the three volumes (2 mm nearest-neighbour resample, ``nan_to_num``, centred zero
+    padding; VolumeDataset.py:214-264, data_util.py:814-828) and ``mri[roi == 0] = 0``
+    (VolumeDataset_ADNI_A4_combined.py:63-68), in ONE kernel launch over the output voxels (``coma_prepare_volumes``).
+
+    Inputs are fp32 CUDA arrays [z, y, x] as ``sitk.GetArrayFromImage`` lays them out (any of them may be None); ``default_value``
+    is what the reference passes as the out-of-image value, ``volume.GetPixelIDValue()`` (8 for float32 images).
+    Returns ``(mri, tau, roi)`` as [1, Z, Y, X] fp32 tensors (None where the input was None).
+    """
+    given = [t for t in (mri, tau, roi) if t is not None]
+    if not given:
+        raise ValueError("prepare_volumes: no volume given")
+    shape = tuple(given[0].shape[-3:])
+    for t in given:
+        if not t.is_cuda:
+            raise RuntimeError("prepare_volumes runs on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.float32 or tuple(t.shape[-3:]) != shape or t.numel() != shape[0] * shape[1] * shape[2]:
+            raise ValueError("prepare_volumes: volumes must be fp32 and share one [z, y, x] shape")
+    res, out, before, ratio = prepare_geometry(shape, spacing, resize, (2.0, 2.0, 2.0), pad_dims)
+    if min(res) <= 0:
+        raise ValueError(f"prepare_volumes: empty resampled volume {res}")
+    srcs = [None if t is None else t.contiguous() for t in (mri, tau, roi)]
+    outs = [None if t is None else torch.empty((1, *out), dtype=torch.float32, device=t.device) for t in (mri, tau, roi)]
+    i3 = C.c_int32 * 3
+    a = _lib.PrepareArgs(*[_lib.ptr(t) for t in srcs], *[_lib.ptr(t) for t in outs], i3(*shape), i3(*res), i3(*out),
+                         i3(*before), (C.c_double * 3)(*ratio), float(default_value))
+    with torch.cuda.device(given[0].device):
+        _lib.call("coma_prepare_volumes", C.byref(a), _lib.stream())
+    return tuple(outs)

@@ -278,6 +278,26 @@ typedef struct {
 } coma_eval_metrics_args;
 int coma_eval_metrics(const coma_eval_metrics_args* a, coma_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * GPU-side input preparation: the step right before the hot path.  Replaces, for one sample, the
+ * SimpleITK nearest-neighbour resample to 2 mm (VolumeDataset.py:236-259), torch.nan_to_num (:226), the centred zero padding
+ * of data_util.pad_volume (data_util.py:814-828) and `mri[roi == 0] = 0` (VolumeDataset_ADNI_A4_combined.py:68) by ONE
+ * kernel over the output voxels.  Arrays are [z, y, x] (the layout of sitk.GetArrayFromImage); per axis a:
+ *   resampled size R_a = round(in_size_a * in_spacing_a / out_spacing_a)   (computed by the caller, numpy round-half-even)
+ *   output voxel o (after padding) -> resampled index r = o - pad_before_a; outside [0, R_a) -> 0
+ *   source index n = floor(r * out_spacing_a / in_spacing_a + 0.5) (ITK's round-half-up nearest index; same origin, same direction,
+ *   identity transform); the voxel is inside iff -0.5 <= r * ratio < in_size_a - 0.5, else it takes default_value
+ * mri / tau / roi may each be NULL (skipped); mri is masked by the resampled roi when both are given.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* mri; const float* tau; const float* roi;   /* [in_size[0], in_size[1], in_size[2]] fp32 */
+  float* mri_out; float* tau_out; float* roi_out;           /* [out_size[0], out_size[1], out_size[2]] fp32 */
+  int32_t in_size[3], res_size[3], out_size[3], pad_before[3];
+  double ratio[3];                                          /* out_spacing / in_spacing per axis */
+  float default_value;                                      /* the reference passes volume.GetPixelIDValue() (8 for float32 images) */
+} coma_prepare_args;
+int coma_prepare_volumes(const coma_prepare_args* a, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -549,3 +549,46 @@ def test_warp_specialised_convs_are_run_to_run_identical(case):
     for _ in range(12):
         y, st = ops.conv_raw(x, wp, None, ksize=k, stride=s, transposed=tr, want_stats=True)
         assert torch.equal(y, y0) and torch.equal(st.sum(dim=1), s0)
+
+
+# ---- input preparation: coma_prepare_volumes against oracle/prepare.py, bit for bit ----
+@pytest.mark.parametrize("shape,spacing,pad_dims,resize", [
+    ((24, 30, 20), (1.0, 1.0, 1.0), (16, 16, 16), True),      # 1 mm -> 2 mm, centred padding, odd pads
+    ((24, 40, 20), (1.0, 1.0, 1.0), (16, 16, 16), True),      # y longer than the target: cropped at its end
+    ((17, 19, 23), (1.2, 0.9, 1.5), (20, 20, 20), True),      # anisotropic, half-integer source coordinates
+    ((9, 7, 11), (4.0, 4.0, 4.0), (24, 24, 24), True),        # coarse -> fine: the last slab falls outside (default value)
+    ((12, 10, 14), (1.0, 1.0, 1.0), (16, 16, 16), False),     # no resample, padding only
+    ((16, 12, 14), (2.0, 2.0, 2.0), (16, 16, 16), True),      # z already at the target: apply_transforms skips the padding
+])
+def test_prepare_volumes_matches_oracle(shape, spacing, pad_dims, resize):
+    import numpy as np
+    from coma_unet_b200 import prepare_volumes
+    from oracle import prepare as oprep
+    g = torch.Generator().manual_seed(sum(shape))
+    mri = torch.rand(shape, generator=g)
+    tau = torch.randn(shape, generator=g)
+    roi = torch.randint(0, 4, shape, generator=g).float() * 1007.0
+    mri.view(-1)[::37] = float("nan"); tau.view(-1)[::41] = float("inf"); tau.view(-1)[::43] = float("-inf")
+    want = oprep.prepare_sample(mri.numpy(), tau.numpy(), roi.numpy(), spacing, resize, pad_dims)
+    got = prepare_volumes(mri.to(DEV), tau.to(DEV), roi.to(DEV), spacing, resize, pad_dims)
+    for w, t, name in zip(want, got, ("mri", "tau", "roi")):
+        assert tuple(t.shape) == tuple(w.shape), name
+        assert np.array_equal(t.cpu().numpy().view(np.uint32), w.numpy().view(np.uint32)), name
+    only_roi = prepare_volumes(None, None, roi.to(DEV), spacing, resize, pad_dims)
+    assert only_roi[0] is None and only_roi[1] is None and torch.equal(only_roi[2], got[2])
+
+
+def test_prepare_volumes_full_size_properties():
+    """BASELINE-size case (a 1 mm 256^3 scan -> the 128^3 the model takes): every other voxel survives, the MRI is zero wherever
+    the ROI map is, the call is idempotent on its own output, and CPU tensors are refused."""
+    from coma_unet_b200 import prepare_volumes
+    g = torch.Generator(device=DEV).manual_seed(5)
+    mri = torch.rand((256, 256, 256), generator=g, device=DEV)
+    roi = (torch.rand((256, 256, 256), generator=g, device=DEV) > 0.3).float() * 17.0
+    m, _, r = prepare_volumes(mri, None, roi, (1.0, 1.0, 1.0))
+    assert m.shape == (1, 128, 128, 128) and torch.equal(r[0], roi[::2, ::2, ::2])
+    assert torch.equal(m[0], mri[::2, ::2, ::2] * (roi[::2, ::2, ::2] != 0))
+    m2, _, r2 = prepare_volumes(m[0], None, r[0], (2.0, 2.0, 2.0))
+    assert torch.equal(m2, m) and torch.equal(r2, r)
+    with pytest.raises(RuntimeError):
+        prepare_volumes(mri.cpu(), None, None)

@@ -114,3 +114,36 @@ def test_metrics_oracle_matches_reference_golden():
         got = ometrics.calc_roi_metrics(common.ROI_INDICES, tau, roi, pred)
         for key, t in zip(("roi_maes", "roi_mapes", "roi_rses", "roi_wrrmses", "roi_nonnan"), got):
             np.testing.assert_allclose(t.double().numpy(), gold[f"{name}/{key}"], rtol=1e-5, equal_nan=True)
+
+
+def test_pad_volume_oracle_matches_reference_golden():
+    """oracle/prepare.py::pad_volume against outputs of the reference's own data_util.pad_volume
+    (tests/golden/make_prepare_golden.py), bit for bit; the host geometry of the CUDA path predicts the same shapes."""
+    import numpy as np
+    from coma_unet_b200 import prepare_geometry
+    from oracle import prepare as oprep
+    from tests.golden import make_prepare_golden as mk
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "prepare_golden.npz"))
+    for name, (shape, target) in mk.CASES.items():
+        got = oprep.pad_volume(target)(mk.case_input(name)).numpy()
+        assert got.shape == gold[name].shape and np.array_equal(got, gold[name]), name
+        if shape[1] != target[-3]:          # apply_transforms pads only then (VolumeDataset.py:261-264)
+            _, out, _, _ = prepare_geometry(shape[1:], (2.0, 2.0, 2.0), True, (2.0, 2.0, 2.0), target)
+            assert tuple(out) == gold[name].shape[1:], name
+
+
+def test_resample_oracle_known_answers():
+    """Known answers of the nearest-neighbour resample (oracle/prepare.py::resize_volume, unpinned restatement of SimpleITK):
+    1 mm -> 2 mm keeps every other voxel, equal spacing is the identity, coarse -> fine repeats voxels, and output voxels whose
+    centre falls outside the image take the default value."""
+    import numpy as np
+    from oracle import prepare as oprep
+    a = np.arange(6 * 8 * 10, dtype=np.float32).reshape(6, 8, 10)
+    assert np.array_equal(oprep.resize_volume(a, (1.0, 1.0, 1.0)), a[::2, ::2, ::2])
+    assert np.array_equal(oprep.resize_volume(a, (2.0, 2.0, 2.0)), a)
+    up = oprep.resize_volume(a, (4.0, 4.0, 4.0), default_value=-1.0)                  # 4 mm -> 2 mm: c = r / 2, floor(c + .5)
+    assert up.shape == (12, 16, 20)
+    assert np.array_equal(up[:-1, :-1, :-1][0::2, 0::2, 0::2], a[:, :, :][:6, :8, :10])
+    assert np.all(up[-1] == -1.0) and np.all(up[:, -1] == -1.0) and np.all(up[:, :, -1] == -1.0)   # c = size - 0.5: outside
+    odd = oprep.resize_volume(np.arange(5, dtype=np.float32).reshape(1, 1, 5), (1.0, 2.0, 2.0))
+    assert odd.shape == (1, 1, 2) and odd.ravel().tolist() == [0.0, 2.0]              # round(2.5) = 2 (numpy half-even)
