@@ -84,8 +84,11 @@ class RnCLoss(nn.Module):
         d = self.label_diff_fn(labels.to(features.dtype))
         logits = self.feature_sim_fn(features) / self.t
         logits = logits - logits.max(dim=1, keepdim=True).values.detach()
-        off = ~torch.eye(n, dtype=torch.bool, device=logits.device)
-        logits, d = logits[off].view(n, n - 1), d[off].view(n, n - 1)
+        # drop the diagonal (the reference's masked_select, :630-633) with a fixed gather: boolean indexing would make the host
+        # wait for the whole forward at this line (nonzero() synchronises), leaving the GPU idle while backward is enqueued
+        j = torch.arange(n - 1, device=logits.device)[None, :]
+        cols = j + (j >= torch.arange(n, device=logits.device)[:, None])
+        logits, d = logits.gather(1, cols), d.gather(1, cols)
         keep = (d[:, None, :] >= d[:, :, None]).to(logits.dtype)
         denom = (keep * logits.exp()[:, None, :]).sum(dim=-1)
         return -((logits - denom.log()) / (n * (n - 1))).sum()

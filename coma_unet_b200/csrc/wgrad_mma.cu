@@ -239,22 +239,174 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(coma_wgrad_args a, i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Second halo variant: the kernel above gives every warp one m16 x n8 tile for all 27 taps, so each x fragment it reads
+// from shared memory feeds ONE mma (about 15 flop per shared-memory byte: ldmatrix bandwidth, not the tensor pipe, bounds it).
+// Here the 27 taps are dealt round-robin to TG = 8 / (CXT / 16) warp groups and a warp owns the whole CGT x 16 tile of its taps:
+// one x fragment (ldmatrix.x4, n16 x k16) feeds CGT / 8 mmas and the g fragments are shared by all taps of the warp
+// (about 26 flop per byte at 32 x 32).  Staging, geometry and the atomic epilogue are those of the kernel above.
+// ------------------------------------------------------------------------------------------------
+template <int CGT, int CXT, int S>
+__global__ void __launch_bounds__(256, (CGT + CXT <= 32 ? 2 : 1)) wgrad_halo_taps_kernel(coma_wgrad_args a, int cx_tiles, int nbw, int nbh, int nbd) {
+  using G = HaloGeo<S>;
+  constexpr int VW = G::VW, VH = G::VH, VD = G::VD, VOX = G::VOX, XW = G::XW, XH = G::XH, XROWS = G::XROWS;
+  constexpr int LDG = CGT + 8, LDX = CXT + 8;
+  constexpr int MI = CGT / 16, NH = CXT / 16, TG = 8 / NH, TPG = (27 + TG - 1) / TG;
+  static_assert(NH == 1 || NH == 2, "warp layout");
+  extern __shared__ __align__(16) uint8_t wsm[];
+  __nv_bfloat16* sg[2];
+  __nv_bfloat16* sx[2];
+  sg[0] = reinterpret_cast<__nv_bfloat16*>(wsm);
+  sx[0] = sg[0] + VOX * LDG;
+  sg[1] = sx[0] + XROWS * LDX;
+  sx[1] = sg[1] + VOX * LDG;
+
+  const int cg0 = (blockIdx.y / cx_tiles) * CGT, cx0 = (blockIdx.y % cx_tiles) * CXT;
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(a.g) + a.g_co + cg0;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(a.x) + a.x_co + cx0;
+  const int nblocks = a.B * nbd * nbh * nbw;
+
+  auto load_block = [&](int buf, int blk) {
+    int t = blk;
+    const int wb = t % nbw; t /= nbw;
+    const int hb = t % nbh; t /= nbh;
+    const int db = t % nbd; t /= nbd;
+    const int64_t b = t;
+    const int w0 = wb * VW, h0 = hb * VH, d0 = db * VD;
+    constexpr int GV = CGT / 8, XV = CXT / 8;
+    for (int i = threadIdx.x; i < VOX * GV; i += 256) {
+      const int row = i / GV, vec = (i % GV) * 8;
+      const int w = w0 + (row % VW), h = h0 + (row / VW) % VH, d = d0 + row / (VW * VH);
+      const bool ok = w < a.Wg && h < a.Hg && d < a.Dg;
+      const __nv_bfloat16* src = ok ? gp + (((b * a.Dg + d) * a.Hg + h) * a.Wg + w) * a.g_cs + vec : gp;
+      cp_async16(sg[buf] + row * LDG + vec, src, ok);
+    }
+    for (int i = threadIdx.x; i < XROWS * XV; i += 256) {
+      const int row = i / XV, vec = (i % XV) * 8;
+      const int w = S * w0 - 1 + (row % XW), h = S * h0 - 1 + (row / XW) % XH, d = S * d0 - 1 + row / (XW * XH);
+      const bool ok = w >= 0 && w < a.Wx && h >= 0 && h < a.Hx && d >= 0 && d < a.Dx;
+      const __nv_bfloat16* src = ok ? xp + (((b * a.Dx + d) * a.Hx + h) * a.Wx + w) * a.x_cs + vec : xp;
+      cp_async16(sx[buf] + row * LDX + vec, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = (warp / NH) & (TG - 1), n0 = (warp % NH) * 16;   // tap group, cx offset of this warp's 16 columns
+  const bool last_tap = q + (TPG - 1) * TG < 27;                // only the last tap slot of a group can be empty
+  static_assert((TPG - 2) * TG + TG - 1 < 27, "tap slots");
+  int tap_off[TPG];                                          // halo-row offset of each of this warp's taps (t = q + j * TG)
+#pragma unroll
+  for (int j = 0; j < TPG; ++j) {
+    const int t = min(q + j * TG, 26);
+    tap_off[j] = ((t / 9) * XH + (t / 3) % 3) * XW + t % 3;
+  }
+  float acc[TPG][MI][2][4];
+#pragma unroll
+  for (int j = 0; j < TPG; ++j)
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][mi][ni][e] = 0.f;
+
+  const int mat = lane >> 3, r = lane & 7;
+  const int g_lane = ((mat >> 1) * 8 + r) * LDG + (mat & 1) * 8;                           // A: (m 0-7|8-15) x (k 0-7|8-15)
+  const int x_lane = ((mat & 1) * (S * XW) + r * S) * LDX + n0 + (mat >> 1) * 8;           // B: (k 0-7, n) (k 8-15, n) (k 0-7, n+8) (k 8-15, n+8)
+
+  int blk = blockIdx.x, it = 0;
+  if (blk < nblocks) load_block(0, blk);
+  for (; blk < nblocks; blk += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = blk + gridDim.x;
+    if (next < nblocks) {
+      load_block(buf ^ 1, next);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const __nv_bfloat16* g_s = sg[buf] + g_lane;
+    const __nv_bfloat16* x_s = sx[buf] + x_lane;
+    // fragments of k-step ks + 1 are fetched while the mmas of k-step ks issue (register double buffer, two k-steps per trip)
+    uint32_t af[2][MI][4], bf[2][TPG][4];
+    auto fetch = [&](int ks, uint32_t (&fa)[MI][4], uint32_t (&fb)[TPG][4]) {
+      const int d = ks / (VH / 2), hp = ks % (VH / 2);           // 16 voxels = two h-lines (2hp, 2hp+1) of plane d
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi) ldsm_x4_t(fa[mi], g_s + ((d * VH + 2 * hp) * VW) * LDG + mi * 16);
+      const __nv_bfloat16* x_k = x_s + ((S * d * XH + S * 2 * hp) * XW) * LDX;
+#pragma unroll
+      for (int j = 0; j < TPG; ++j)
+        if (j < TPG - 1 || last_tap) ldsm_x4_t(fb[j], x_k + tap_off[j] * LDX);
+    };
+    auto issue = [&](const uint32_t (&fa)[MI][4], const uint32_t (&fb)[TPG][4]) {
+#pragma unroll
+      for (int j = 0; j < TPG; ++j)
+        if (j < TPG - 1 || last_tap) {
+#pragma unroll
+          for (int mi = 0; mi < MI; ++mi) {
+            mma_bf16(acc[j][mi][0], fa[mi], fb[j][0], fb[j][1]);
+            mma_bf16(acc[j][mi][1], fa[mi], fb[j][2], fb[j][3]);
+          }
+        }
+    };
+    static_assert((VOX / 16) % 2 == 0, "two k-steps per trip");
+    fetch(0, af[0], bf[0]);
+#pragma unroll 1
+    for (int ks = 0; ks < VOX / 16; ks += 2) {
+      fetch(ks + 1, af[1], bf[1]);
+      issue(af[0], bf[0]);
+      if (ks + 2 < VOX / 16) fetch(ks + 2, af[0], bf[0]);
+      issue(af[1], bf[1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < TPG; ++j) {
+    const int t = q + j * TG;
+    if (t < 27) {
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int cg = cg0 + mi * 16 + (lane >> 2) + (e >> 1) * 8;
+            const int cx = cx0 + n0 + ni * 8 + (lane & 3) * 2 + (e & 1);
+            atomicAdd(a.dw + ((int64_t)t * a.Cg + cg) * a.Cx + cx, acc[j][mi][ni][e]);
+          }
+    }
+  }
+}
+
 template <int CGT, int CXT, int S = 1>
 int launch_wgrad_halo(const coma_wgrad_args& a, cudaStream_t stream) {
   using G = HaloGeo<S>;
   constexpr int VW = G::VW, VH = G::VH, VD = G::VD, VOX = G::VOX, XROWS = G::XROWS;
   constexpr int LDG = CGT + 8, LDX = CXT + 8;
   const size_t smem = (size_t)2 * (VOX * LDG + XROWS * LDX) * sizeof(__nv_bfloat16);
+  static const bool v1 = [] { const char* e = getenv("COMA_WGRAD_HALO_V1"); return e && e[0] == '1'; }();   // the one-tile-per-warp kernel
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(wgrad_halo_kernel<CGT, CXT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  static int resident = 1;       // CTAs of the tap-split kernel that fit one SM (the narrow tiles leave room for two)
+  if (!set) {
+    cudaFuncSetAttribute(wgrad_halo_kernel<CGT, CXT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wgrad_halo_taps_kernel<CGT, CXT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, wgrad_halo_taps_kernel<CGT, CXT, S>, 256, smem) != cudaSuccess || resident < 1)
+      resident = 1;
+    if (resident > 2) resident = 2;
+    set = true;
+  }
   const int nbw = (a.Wg + VW - 1) / VW, nbh = (a.Hg + VH - 1) / VH, nbd = (a.Dg + VD - 1) / VD;
   const int nblocks = a.B * nbw * nbh * nbd;
   const int cg_tiles = a.Cg / CGT, cx_tiles = a.Cx / CXT;
-  int gx = num_sms() / (cg_tiles * cx_tiles);
+  int gx = num_sms() * (v1 ? 1 : resident) / (cg_tiles * cx_tiles);
   if (gx < 1) gx = 1;
   if (gx > nblocks) gx = nblocks;
   dim3 grid((unsigned)gx, (unsigned)(cg_tiles * cx_tiles));
-  wgrad_halo_kernel<CGT, CXT, S><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
+  if (v1) wgrad_halo_kernel<CGT, CXT, S><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
+  else wgrad_halo_taps_kernel<CGT, CXT, S><<<grid, 256, smem, stream>>>(a, cx_tiles, nbw, nbh, nbd);
   COMA_CHECK_LAUNCH("wgrad_halo");
   return COMA_OK;
 }

@@ -315,7 +315,11 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
             flags = getattr(self, "_host_flags", None)
             if flags is None:
                 flags = (cov0 == 1).cpu()
-            used = (bool(flags.any()), bool((~flags).any()))
+            if isinstance(flags, tuple):     # device covariates: the read-back issued by forward() is resolved in backward
+                host, landed = flags
+                used = lambda: (landed.synchronize(), (bool(host.any()), bool((~host).any())))[1]
+            else:
+                used = (bool(flags.any()), bool((~flags).any()))
         # channel padding of the two small inputs: 16 for the per-tap tensor-core path; without autograd the tap-packed
         # kernel takes them as 4 (3 + one zero) and 2 channels
         slim = getattr(self, "slim_inputs", False) and not torch.is_grad_enabled() and dt == torch.bfloat16 and ops.taps_conv_ok(out)
@@ -332,6 +336,14 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         if covariate is not None:   # one H2D copy / cast per forward instead of one per conditioned layer
             if not covariate.is_cuda:
                 self._host_flags = covariate.reshape(covariate.shape[0], -1)[:, 0] == 1     # no device sync needed
+            elif torch.is_grad_enabled():
+                # covariates already on the device: read the positive/negative flags back into pinned memory now and look at
+                # them only in backward (ops.RoiPaintFn), so that the forward never waits for the GPU
+                host = torch.empty(covariate.shape[0], dtype=torch.bool, pin_memory=True)
+                host.copy_(covariate.reshape(covariate.shape[0], -1)[:, 0] == 1, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record()
+                self._host_flags = (host, landed)
             covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
         with blocks.bn_updates(2):   # the reference's duplicated backbone pass (:664,666) in closed form

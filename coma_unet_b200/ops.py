@@ -571,8 +571,9 @@ class RoiPaintFn(torch.autograd.Function):
         L.call("coma_roi_paint_bwd", L.ptr(dout), L.ptr(is_pos), L.ptr(d[0]), L.ptr(d[1]), B, V, vol_cs(dout),
                L.dtype_code(dout.dtype), L.stream())
         # a prompt no sample selected keeps grad None (reference: attn_unet_data_parallel.py:639; SURVEY hard part 5)
-        dpos = d[0].reshape(ctx.pshape) if ctx.used[0] else None
-        dneg = d[1].reshape(ctx.pshape) if ctx.used[1] else None
+        used = ctx.used() if callable(ctx.used) else ctx.used
+        dpos = d[0].reshape(ctx.pshape) if used[0] else None
+        dneg = d[1].reshape(ctx.pshape) if used[1] else None
         return dpos, dneg, None, None, None, None, None, None, None, None
 
 

@@ -37,6 +37,9 @@ for _ in range(3):
 t_launch = time.perf_counter() - t0
 torch.cuda.synchronize()
 t_total = time.perf_counter() - t0
+st = torch.cuda.memory_stats()
+print(f"max allocated {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB, "
+      f"alloc retries {st.get('num_alloc_retries')}, cudaMalloc calls {st.get('segment.all.allocated')}")
 print(f"B={B}: host launch time {t_launch / 3 * 1e3:.1f} ms/step, wall {t_total / 3 * 1e3:.1f} ms/step")
 pr = cProfile.Profile()
 pr.enable()
