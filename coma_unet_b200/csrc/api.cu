@@ -21,6 +21,8 @@ int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream);
 int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool wgrad_mma_supported(const coma_wgrad_args& a);
 int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream);
+bool wgrad_tc_supported(const coma_wgrad_args& a);
+int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool conv_tc_supported(const coma_conv_args& a);
 int conv_tc_stat_chunks(const coma_conv_args& a);
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream);
@@ -121,6 +123,7 @@ static int check_wgrad(const coma_wgrad_args* a, const char* who) {
   return COMA_OK;
 }
 static int run_wgrad(const coma_wgrad_args* a, cudaStream_t stream) {
+  if (a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a)) return wgrad_tc_launch(*a, stream);      // tcgen05 (k3 s1, 32-channel multiples)
   if (a->impl != COMA_IMPL_SIMT && wgrad_mma_supported(*a)) return wgrad_mma_launch(*a, stream);
   return wgrad_simt_launch(*a, stream);
 }

@@ -2108,6 +2108,12 @@ int launch_halo(const coma_conv_args& a, const HaloPlan& h, const CUtensorMap& t
 
 }  // namespace
 
+// cached cuTensorMapEncodeTiled for bf16 tensors, for the other translation units (wgrad_tc.cu)
+bool tensor_map_bf16(CUtensorMap* out, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, const cuuint32_t* estr, int swz) {
+  return make_map(out, base, rank, dims, strides_bytes, box, estr, swz);
+}
+
 // ---- CTA-pair kernel planning ----
 struct PairPlan { bool ok; int cols_w, cols_h, segs_d, DS, nslab, KCH, KC, NT, EPI, CPS; uint32_t rowb, slab_bytes, chunk_bytes, w_bytes; size_t smem; };
 

@@ -1,0 +1,281 @@
+// Weight gradient of the 3x3x3 stride-1 convolutions on the 5th-generation tensor cores (tcgen05 / TMEM, sm_100a):
+//     dw[kd,kh,kw][cg][cx] += sum_v g[v][cg] * x[v + (kd-1, kh-1, kw-1)][cx]
+// Replaces cuDNN wgrad behind loss.backward() (attn_unet_data_parallel.py:884) for the Conv3d layers whose channels are
+// multiples of 32 (ConvBlock convs and AttentionLayer.merge, :285-306 and MONAI's attentionunet).
+//
+// GEMM view.  K = voxels.  Both operands are read straight out of the NDHWC activations, i.e. MN-major (a shared-memory
+// row = one voxel, 32 channels = 64 bytes, 64B swizzle as written by TMA): profiles/r01_probe_mn_major_operand.log shows
+// that an MN-major descriptor may start at any row, that LBO strides the 32-channel chunks of the M / N extent and SBO the
+// 8-row K groups, and that the chunk stride may be a single row.  So ONE tcgen05.mma (M = 128, N = 96, K = 16 voxels of a
+// W line) produces nine filter taps at once:
+//     A = x slab, 4 chunks one row apart       -> M = (kw = 0, 1, 2, [unused]) x 32 input channels
+//     B = g slab, 3 chunks one H line apart    -> N = (kh = 2, 1, 0) x 32 output-gradient channels
+// (substituting u = v + (0, kh-1, 0) moves the kh shift onto g: dw = sum_u g[u - (0, kh-1, 0)] * x[u + (kd-1, 0, kw-1)]),
+// and kd selects one of three TMEM accumulators fed from the x planes d-1, d, d+1.  128 x 96 x 16 issues in 56 cycles
+// (profiles/r01_probe_mma_rate_layout_sbo.log), 3/4 of the M rows are useful.
+//
+// A CTA owns one (32 input channels) x (32 gradient channels) pair and marches along D through [8 lines x 32 voxels]
+// columns of the volume: per plane one TMA box of x (8 lines x 36 rows, W halo, zero fill = conv padding) and one of g
+// (10 lines x 32 rows, H halo) go into a ring of four slots; plane d's MMAs read the x slots d-1, d, d+1, so every plane
+// is fetched once.  The three [128 x 96] fp32 accumulators stay in TMEM for the CTA's whole life and are added into dw
+// with fp32 atomics at the end (the same contract as the mma.sync kernels in wgrad_mma.cu).
+// Warp roles (192 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <cuda.h>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace coma {
+
+bool tensor_map_bf16(CUtensorMap* out, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, const cuuint32_t* estr, int swz);
+
+namespace {
+
+constexpr int BH = 8, BW = 32;                  // voxel column: 8 lines x 32 voxels per plane
+constexpr int XR = BW + 4;                      // x rows per line: W halo + the rows the unused fourth chunk touches
+constexpr int GL = BH + 2;                      // g lines per plane: H halo
+constexpr int ROWB = 64;                        // bytes per row: 32 bf16 channels
+constexpr uint32_t X_BYTES = BH * XR * ROWB;    // 18432
+constexpr uint32_t G_BYTES = GL * BW * ROWB;    // 20480
+constexpr uint32_t SLOT_BYTES = X_BYTES + G_BYTES;
+constexpr int RING = 4;
+constexpr int ACC_COLS = 96;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int kThreads = 192;
+
+struct WgParams {
+  float* dw;
+  int B, D, H, W, Cg, Cx;
+  int cg_tiles, cx_slabs;
+  int DC, nd, nh, nw, items;                    // depth chunk, chunks / columns per axis, work items per channel pair
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();            // a lost TMA / MMA completion must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(s32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_lane() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// MN-major operand descriptor, 64B swizzle: LBO = stride between 32-channel chunks, SBO = stride between 8-row K groups
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                       // 64B swizzle
+  return d;
+}
+
+struct Item { int b, d0, nd, h0, w0; };
+__device__ __forceinline__ Item decode_item(const WgParams& p, int it) {
+  Item r;
+  const int wb = it % p.nw; it /= p.nw;
+  const int hb = it % p.nh; it /= p.nh;
+  const int db = it % p.nd; it /= p.nd;
+  r.b = it;
+  r.d0 = db * p.DC;
+  r.nd = min(p.DC, p.D - r.d0);
+  r.h0 = hb * BH;
+  r.w0 = wb * BW;
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                                                               const WgParams p) {
+  extern __shared__ uint8_t wg_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING * SLOT_BYTES);
+  uint64_t* empty = full + RING;
+  uint64_t* done = empty + RING;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y, cg0 = (pair / p.cx_slabs) * 32, cx0 = (pair % p.cx_slabs) * 32;
+  const bool has_work = (int)blockIdx.x < p.items;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { bar_init(full + i, 1); bar_init(empty + i, 1); }
+    bar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: planes d0-1 .. d0+nd of every item
+    if (elect_lane()) {
+      uint32_t n = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const Item c = decode_item(p, it);
+        for (int pl = -1; pl <= c.nd; ++pl, ++n) {
+          const int slot = n % RING;
+          bar_wait(empty + slot, ((n / RING) & 1) ^ 1);
+          uint8_t* dst = smem + slot * SLOT_BYTES;
+          const bool with_g = pl >= 0 && pl < c.nd;
+          bar_expect_tx(full + slot, with_g ? SLOT_BYTES : X_BYTES);
+          tma_5d(dst, &tmX, full + slot, cx0, c.w0 - 1, c.h0, c.d0 + pl, c.b);
+          if (with_g) tma_5d(dst + X_BYTES, &tmG, full + slot, cg0, c.w0, c.h0 - 1, c.d0 + pl, c.b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_lane()) {
+      // D f32, A / B bf16, both MN-major (bits 15, 16), N = 96, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t base = s32(smem);
+      uint32_t n0 = 0, started = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const Item c = decode_item(p, it);
+        for (int t = 0; t < c.nd; ++t) {
+          // loads n0 + t, n0 + t + 1, n0 + t + 2 hold the x planes d-1, d, d+1; n0 + t + 1 also holds g(d)
+          if (t == 0) {
+            bar_wait(full + (n0 % RING), (n0 / RING) & 1);
+            bar_wait(full + ((n0 + 1) % RING), ((n0 + 1) / RING) & 1);
+          }
+          bar_wait(full + ((n0 + t + 2) % RING), ((n0 + t + 2) / RING) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t gbase = base + ((n0 + t + 1) % RING) * SLOT_BYTES + X_BYTES;
+#pragma unroll 1
+          for (int ks = 0; ks < BH * (BW / 16); ++ks) {
+            const int hl = ks >> 1, seg = ks & 1;
+            const uint64_t bdesc = mn_desc(gbase + (uint32_t)(hl * BW + seg * 16) * ROWB, BW * ROWB, 8 * ROWB);
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+              const uint32_t xbase = base + ((n0 + t + kd) % RING) * SLOT_BYTES;
+              const uint64_t adesc = mn_desc(xbase + (uint32_t)(hl * XR + seg * 16) * ROWB, ROWB, 8 * ROWB);
+              mma_bf16_ss(tmem + kd * ACC_COLS, adesc, bdesc, idesc, started);
+            }
+            started = 1;
+          }
+          commit_to(empty + ((n0 + t) % RING));                    // plane d-1 is not needed again
+        }
+        commit_to(empty + ((n0 + c.nd) % RING));                   // the last two planes of the item
+        commit_to(empty + ((n0 + c.nd + 1) % RING));
+        n0 += c.nd + 2;
+      }
+      commit_to(done);
+    }
+  } else if (has_work) {
+    // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dw[tap][Cg][Cx]
+    bar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int kw = warp & 3;                                        // TMEM lane quadrant of this warp = its 32 M rows
+    if (kw < 3) {
+#pragma unroll 1
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+          const int tap = (kd * 3 + (2 - j)) * 3 + kw;
+          float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + lane;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[16];
+            tmem_ld16(tmem + ((uint32_t)(kw * 32) << 16) + kd * ACC_COLS + j * 32 + half * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(half * 16 + i) * p.Cx, __uint_as_float(v[i]));
+          }
+        }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const coma_wgrad_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_TC"); return e && e[0] == '1'; }();
+  return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Cg % 32 == 0 && a.Cx % 32 == 0 &&
+         a.Wg % BW == 0 && a.Hg % BH == 0 && a.Dg >= 4 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15) == 0;
+}
+
+int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  CUtensorMap tmX, tmG;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cx, (cuuint64_t)a.Wx, (cuuint64_t)a.Hx, (cuuint64_t)a.Dx, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wx * a.x_cs * 2, (cuuint64_t)a.Hx * a.Wx * a.x_cs * 2,
+                             (cuuint64_t)a.Dx * a.Hx * a.Wx * a.x_cs * 2};
+    cuuint32_t box[5] = {32, XR, BH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
+    if (!tensor_map_bf16(&tmX, base, 5, dims, strides, box, estr, ROWB)) return COMA_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cg, (cuuint64_t)a.Wg, (cuuint64_t)a.Hg, (cuuint64_t)a.Dg, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.g_cs * 2, (cuuint64_t)a.Wg * a.g_cs * 2, (cuuint64_t)a.Hg * a.Wg * a.g_cs * 2,
+                             (cuuint64_t)a.Dg * a.Hg * a.Wg * a.g_cs * 2};
+    cuuint32_t box[5] = {32, BW, GL, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.g) + a.g_co));
+    if (!tensor_map_bf16(&tmG, base, 5, dims, strides, box, estr, ROWB)) return COMA_ERR_CUDA;
+  }
+  WgParams p{};
+  p.dw = a.dw;
+  p.B = a.B; p.D = a.Dg; p.H = a.Hg; p.W = a.Wg; p.Cg = a.Cg; p.Cx = a.Cx;
+  p.cg_tiles = a.Cg / 32;
+  p.cx_slabs = a.Cx / 32;
+  p.nh = a.Hg / BH;
+  p.nw = a.Wg / BW;
+  const int pairs = p.cg_tiles * p.cx_slabs;
+  int gx = num_sms() / pairs;
+  if (gx < 1) gx = 1;
+  // depth chunks: long marches amortise the two halo planes; shorter ones balance the CTAs of a channel pair
+  p.DC = a.Dg;
+  while (p.DC > 8 && (int64_t)a.B * ((a.Dg + p.DC - 1) / p.DC) * p.nh * p.nw < (int64_t)4 * gx) p.DC = (p.DC + 1) / 2;
+  p.nd = (a.Dg + p.DC - 1) / p.DC;
+  p.items = a.B * p.nd * p.nh * p.nw;
+  if (gx > p.items) gx = p.items;
+  const size_t smem = (size_t)RING * SLOT_BYTES + 1024 + 256;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  dim3 grid((unsigned)gx, (unsigned)pairs);
+  wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+  COMA_CHECK_LAUNCH("wgrad_tc");
+  return COMA_OK;
+}
+
+}  // namespace coma

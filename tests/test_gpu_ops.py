@@ -67,6 +67,10 @@ CONV_CASES = [
     (1, 16, 32, 18, 20, 22, 3, 2, False),   # ragged blocks in every dim
     (1, 32, 16, 8, 8, 8, 3, 2, True),
     (2, 64, 32, 9, 10, 12, 3, 2, True),
+    # tcgen05 weight gradient (k3 s1, channels multiples of 32, W % 32 == 0, H % 8 == 0): MN-major operands, nine taps per MMA
+    (1, 32, 32, 5, 8, 32, 3, 1, False),     # one column, one channel pair
+    (2, 64, 32, 9, 16, 64, 3, 1, False),    # two x slabs, several columns, odd depth (ragged depth chunks)
+    (1, 32, 128, 20, 24, 32, 3, 1, False),  # four gradient tiles, depth split into chunks
 ]
 
 
