@@ -75,7 +75,21 @@ __global__ void __launch_bounds__(kThreads) reduce_vec_kernel(const T* __restric
   const T* dyb = NQ == 3 ? static_cast<const T*>(ctx.dy) + (int64_t)b * V * ctx.dy_cs + ctx.dy_co + cvec * 8 : nullptr;
   const T* rb = (NQ == 3 && ctx.r) ? static_cast<const T*>(ctx.r) + (int64_t)b * V * ctx.r_cs + cvec * 8 : nullptr;
   if (vlane < lanes) {
-    for (int64_t v = v0 + vlane; v < v1; v += lanes) {
+    int64_t v = v0 + vlane;
+    // two voxels per trip: all loads of both are issued before the first accumulate (the sweep is latency- not issue-bound)
+    for (; v + lanes < v1; v += 2 * lanes) {
+      float xv[8], dyv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float xw[8], dyw[8], rw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      load8(xb + v * cs, xv);
+      load8(xb + (v + lanes) * cs, xw);
+      if (NQ == 3) load8(dyb + v * ctx.dy_cs, dyv);
+      if (NQ == 3) load8(dyb + (v + lanes) * ctx.dy_cs, dyw);
+      if (NQ == 3 && rb) load8(rb + v * ctx.r_cs, rv);
+      if (NQ == 3 && rb) load8(rb + (v + lanes) * ctx.r_cs, rw);
+      accumulate8<T, NQ, SIMPLE>(xv, dyv, rv, A8, S8, M8, R8, ctx.act, slope, acc);
+      accumulate8<T, NQ, SIMPLE>(xw, dyw, rw, A8, S8, M8, R8, ctx.act, slope, acc);
+    }
+    if (v < v1) {
       float xv[8], dyv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       load8(xb + v * cs, xv);
       if (NQ == 3) load8(dyb + v * ctx.dy_cs, dyv);

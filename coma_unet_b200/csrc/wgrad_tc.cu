@@ -32,15 +32,20 @@ bool tensor_map_bf16(CUtensorMap* out, void* base, int rank, const cuuint64_t* d
 
 namespace {
 
-constexpr int BH = 8, BW = 32;                  // voxel column: 8 lines x 32 voxels per plane
-constexpr int XR = BW + 4;                      // x rows per line: W halo + the rows the unused fourth chunk touches
-constexpr int GL = BH + 2;                      // g lines per plane: H halo
-constexpr int ROWB = 64;                        // bytes per row: 32 bf16 channels
-constexpr uint32_t X_BYTES = BH * XR * ROWB;    // 18432
-constexpr uint32_t G_BYTES = GL * BW * ROWB;    // 20480
-constexpr uint32_t SLOT_BYTES = X_BYTES + G_BYTES;
+// CHX / CHG: channels per x / g row (32 -> 64B swizzle, 16 -> 32B swizzle); BW: voxels per line of a column (W % BW == 0)
+template <int CHX, int CHG, int BW>
+struct Geo {
+  static constexpr int BH = 256 / BW;                         // lines per column: 256 voxels per plane
+  static constexpr int MCH = 128 / CHX;                       // row-shifted chunks in M (3 useful)
+  static constexpr int XR = BW + MCH;                         // x rows per line: W halo + the rows the unused chunks touch
+  static constexpr int GL = BH + 2;                           // g lines per plane: H halo
+  static constexpr int ROWBX = CHX * 2, ROWBG = CHG * 2;      // bytes per row
+  static constexpr uint32_t X_BYTES = BH * XR * ROWBX, G_BYTES = GL * BW * ROWBG, SLOT_BYTES = X_BYTES + G_BYTES;
+  static constexpr int ACC_COLS = 3 * CHG;                    // N = (kh = 2, 1, 0) x CHG
+  static constexpr int KSTEPS = 256 / 16, SEGS = BW / 16;
+  static_assert(X_BYTES % 1024 == 0 && G_BYTES % 1024 == 0, "slots keep the swizzle phase");
+};
 constexpr int RING = 4;
-constexpr int ACC_COLS = 96;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int kThreads = 192;
 
@@ -89,18 +94,20 @@ __device__ __forceinline__ bool elect_lane() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// MN-major operand descriptor, 64B swizzle: LBO = stride between 32-channel chunks, SBO = stride between 8-row K groups
+// MN-major operand descriptor (rows of ROWB bytes = the swizzle span): LBO = stride between chunks, SBO = stride between 8-row K groups
+template <int ROWB>
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t)4 << 61;                       // 64B swizzle
+  d |= (uint64_t)(ROWB == 64 ? 4 : 6) << 61;    // 64B / 32B swizzle
   return d;
 }
 
 struct Item { int b, d0, nd, h0, w0; };
+template <int BH, int BW>
 __device__ __forceinline__ Item decode_item(const WgParams& p, int it) {
   Item r;
   const int wb = it % p.nw; it /= p.nw;
@@ -114,8 +121,12 @@ __device__ __forceinline__ Item decode_item(const WgParams& p, int it) {
   return r;
 }
 
+template <int CHX, int CHG, int BW>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                                                                const WgParams p) {
+  using G = Geo<CHX, CHG, BW>;
+  constexpr int BH = G::BH, XR = G::XR, ROWBX = G::ROWBX, ROWBG = G::ROWBG, ACC_COLS = G::ACC_COLS;
+  constexpr uint32_t X_BYTES = G::X_BYTES, SLOT_BYTES = G::SLOT_BYTES;
   extern __shared__ uint8_t wg_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING * SLOT_BYTES);
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.y, cg0 = (pair / p.cx_slabs) * 32, cx0 = (pair % p.cx_slabs) * 32;
+  const int pair = blockIdx.y, cg0 = (pair / p.cx_slabs) * CHG, cx0 = (pair % p.cx_slabs) * CHX;
   const bool has_work = (int)blockIdx.x < p.items;
 
   if (threadIdx.x == 0) {
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     if (elect_lane()) {
       uint32_t n = 0;
       for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-        const Item c = decode_item(p, it);
+        const Item c = decode_item<BH, BW>(p, it);
         for (int pl = -1; pl <= c.nd; ++pl, ++n) {
           const int slot = n % RING;
           bar_wait(empty + slot, ((n / RING) & 1) ^ 1);
@@ -161,12 +172,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (elect_lane()) {
-      // D f32, A / B bf16, both MN-major (bits 15, 16), N = 96, M = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+      // D f32, A / B bf16, both MN-major (bits 15, 16), N = 3 * CHG, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (((uint32_t)ACC_COLS >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t base = s32(smem);
       uint32_t n0 = 0, started = 0;
       for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-        const Item c = decode_item(p, it);
+        const Item c = decode_item<BH, BW>(p, it);
         for (int t = 0; t < c.nd; ++t) {
           // loads n0 + t, n0 + t + 1, n0 + t + 2 hold the x planes d-1, d, d+1; n0 + t + 1 also holds g(d)
           if (t == 0) {
@@ -177,13 +188,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t gbase = base + ((n0 + t + 1) % RING) * SLOT_BYTES + X_BYTES;
 #pragma unroll 1
-          for (int ks = 0; ks < BH * (BW / 16); ++ks) {
-            const int hl = ks >> 1, seg = ks & 1;
-            const uint64_t bdesc = mn_desc(gbase + (uint32_t)(hl * BW + seg * 16) * ROWB, BW * ROWB, 8 * ROWB);
+          for (int ks = 0; ks < G::KSTEPS; ++ks) {
+            const int hl = ks / G::SEGS, seg = ks % G::SEGS;
+            const uint64_t bdesc = mn_desc<ROWBG>(gbase + (uint32_t)(hl * BW + seg * 16) * ROWBG, BW * ROWBG, 8 * ROWBG);
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
               const uint32_t xbase = base + ((n0 + t + kd) % RING) * SLOT_BYTES;
-              const uint64_t adesc = mn_desc(xbase + (uint32_t)(hl * XR + seg * 16) * ROWB, ROWB, 8 * ROWB);
+              const uint64_t adesc = mn_desc<ROWBX>(xbase + (uint32_t)(hl * XR + seg * 16) * ROWBX, ROWBX, 8 * ROWBX);
               mma_bf16_ss(tmem + kd * ACC_COLS, adesc, bdesc, idesc, started);
             }
             started = 1;
@@ -200,23 +211,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dw[tap][Cg][Cx]
     bar_wait(done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int kw = warp & 3;                                        // TMEM lane quadrant of this warp = its 32 M rows
-    if (kw < 3) {
+    const int m = (warp & 3) * 32 + lane;                           // TMEM lane = M row = kw * CHX + input channel
+    const int kw = m / CHX, cxl = m % CHX;
 #pragma unroll 1
-      for (int kd = 0; kd < 3; ++kd)
+    for (int kd = 0; kd < 3; ++kd)
 #pragma unroll 1
-        for (int j = 0; j < 3; ++j) {
-          const int tap = (kd * 3 + (2 - j)) * 3 + kw;
-          float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + lane;
+      for (int j = 0; j < 3; ++j) {
+        const int tap = (kd * 3 + (2 - j)) * 3 + (kw < 3 ? kw : 0);
+        float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + cxl;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[16];
-            tmem_ld16(tmem + ((uint32_t)(kw * 32) << 16) + kd * ACC_COLS + j * 32 + half * 16, v);
+        for (int part = 0; part < CHG / 16; ++part) {
+          uint32_t v[16];
+          tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kd * ACC_COLS + j * CHG + part * 16, v);   // warp-collective
+          if (kw < 3) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(half * 16 + i) * p.Cx, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
           }
         }
-    }
+      }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -226,39 +238,35 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
 }  // namespace
 
-bool wgrad_tc_supported(const coma_wgrad_args& a) {
-  static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_TC"); return e && e[0] == '1'; }();
-  return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Cg % 32 == 0 && a.Cx % 32 == 0 &&
-         a.Wg % BW == 0 && a.Hg % BH == 0 && a.Dg >= 4 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
-         ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15) == 0;
-}
-
-int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+namespace {
+template <int CHX, int CHG, int BW>
+int launch_wgrad_tc(const coma_wgrad_args& a, cudaStream_t stream) {
+  using G = Geo<CHX, CHG, BW>;
   CUtensorMap tmX, tmG;
   {
     cuuint64_t dims[5] = {(cuuint64_t)a.Cx, (cuuint64_t)a.Wx, (cuuint64_t)a.Hx, (cuuint64_t)a.Dx, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wx * a.x_cs * 2, (cuuint64_t)a.Hx * a.Wx * a.x_cs * 2,
                              (cuuint64_t)a.Dx * a.Hx * a.Wx * a.x_cs * 2};
-    cuuint32_t box[5] = {32, XR, BH, 1, 1};
+    cuuint32_t box[5] = {CHX, G::XR, G::BH, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
-    if (!tensor_map_bf16(&tmX, base, 5, dims, strides, box, estr, ROWB)) return COMA_ERR_CUDA;
+    if (!tensor_map_bf16(&tmX, base, 5, dims, strides, box, estr, G::ROWBX)) return COMA_ERR_CUDA;
   }
   {
     cuuint64_t dims[5] = {(cuuint64_t)a.Cg, (cuuint64_t)a.Wg, (cuuint64_t)a.Hg, (cuuint64_t)a.Dg, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.g_cs * 2, (cuuint64_t)a.Wg * a.g_cs * 2, (cuuint64_t)a.Hg * a.Wg * a.g_cs * 2,
                              (cuuint64_t)a.Dg * a.Hg * a.Wg * a.g_cs * 2};
-    cuuint32_t box[5] = {32, BW, GL, 1, 1};
+    cuuint32_t box[5] = {CHG, BW, G::GL, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.g) + a.g_co));
-    if (!tensor_map_bf16(&tmG, base, 5, dims, strides, box, estr, ROWB)) return COMA_ERR_CUDA;
+    if (!tensor_map_bf16(&tmG, base, 5, dims, strides, box, estr, G::ROWBG)) return COMA_ERR_CUDA;
   }
   WgParams p{};
   p.dw = a.dw;
   p.B = a.B; p.D = a.Dg; p.H = a.Hg; p.W = a.Wg; p.Cg = a.Cg; p.Cx = a.Cx;
-  p.cg_tiles = a.Cg / 32;
-  p.cx_slabs = a.Cx / 32;
-  p.nh = a.Hg / BH;
+  p.cg_tiles = a.Cg / CHG;
+  p.cx_slabs = a.Cx / CHX;
+  p.nh = a.Hg / G::BH;
   p.nw = a.Wg / BW;
   const int pairs = p.cg_tiles * p.cx_slabs;
   int gx = num_sms() / pairs;
@@ -269,13 +277,32 @@ int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {
   p.nd = (a.Dg + p.DC - 1) / p.DC;
   p.items = a.B * p.nd * p.nh * p.nw;
   if (gx > p.items) gx = p.items;
-  const size_t smem = (size_t)RING * SLOT_BYTES + 1024 + 256;
+  const size_t smem = (size_t)RING * G::SLOT_BYTES + 1024 + 256;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(wgrad_tc_kernel<CHX, CHG, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   dim3 grid((unsigned)gx, (unsigned)pairs);
-  wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+  wgrad_tc_kernel<CHX, CHG, BW><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   COMA_CHECK_LAUNCH("wgrad_tc");
   return COMA_OK;
+}
+}  // namespace
+
+bool wgrad_tc_supported(const coma_wgrad_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_TC"); return e && e[0] == '1'; }();
+  const bool lines = (a.Wg % 32 == 0 && a.Hg % 8 == 0) || (a.Wg == 16 && a.Hg % 16 == 0);
+  return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && lines &&
+         a.Dg >= 4 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15) == 0;
+}
+
+int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  const bool x32 = a.Cx % 32 == 0, g32 = a.Cg % 32 == 0, w32 = a.Wg % 32 == 0;
+#define COMA_WGTC_CASE(XV, GV, WV) if (x32 == (XV == 32) && g32 == (GV == 32) && w32 == (WV == 32)) return launch_wgrad_tc<XV, GV, WV>(a, stream);
+  COMA_WGTC_CASE(32, 32, 32) COMA_WGTC_CASE(32, 16, 32) COMA_WGTC_CASE(16, 32, 32) COMA_WGTC_CASE(16, 16, 32)
+  COMA_WGTC_CASE(32, 32, 16) COMA_WGTC_CASE(32, 16, 16) COMA_WGTC_CASE(16, 32, 16) COMA_WGTC_CASE(16, 16, 16)
+#undef COMA_WGTC_CASE
+  set_error("wgrad_tc: unsupported shape");
+  return COMA_ERR_UNSUPPORTED;
 }
 
 }  // namespace coma

@@ -71,6 +71,10 @@ CONV_CASES = [
     (1, 32, 32, 5, 8, 32, 3, 1, False),     # one column, one channel pair
     (2, 64, 32, 9, 16, 64, 3, 1, False),    # two x slabs, several columns, odd depth (ragged depth chunks)
     (1, 32, 128, 20, 24, 32, 3, 1, False),  # four gradient tiles, depth split into chunks
+    (1, 16, 16, 5, 8, 32, 3, 1, False),     # 16-channel rows on both operands (32B swizzle, eight row-shifted chunks in M)
+    (2, 32, 16, 5, 16, 32, 3, 1, False),    # mixed row widths
+    (1, 16, 32, 4, 8, 64, 3, 1, False),
+    (2, 32, 64, 16, 16, 16, 3, 1, False),   # 16-voxel lines (the 16^3 level): 16 lines x 16 voxels per plane
 ]
 
 
