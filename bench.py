@@ -320,7 +320,7 @@ def run_ours(args):
         model.train(True)
         crit = build_criterion()
         engine = DataParallelEngine(model, world_size=world)
-        opt = torch.optim.AdamW(model.parameters(), 1e-3)
+        opt = torch.optim.AdamW(model.parameters(), 1e-3, fused=True)     # the same optimizer train_dp builds
 
         def step(m=mri, t=tau, r=roi, c=covars):
             opt.zero_grad(set_to_none=True)

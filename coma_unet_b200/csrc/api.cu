@@ -28,6 +28,7 @@ int conv_tc_stat_chunks(const coma_conv_args& a);
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream);
 bool conv_tc_prologue_supported(const coma_conv_args& a);
 bool conv_simt_prologue_fused(const coma_conv_args& a);
+bool conv_simt_preferred(const coma_conv_args& a);
 
 static int check_conv(const coma_conv_args* a, const char* who) {
   COMA_CHECK_ARG(a && a->x && a->w && a->y, "%s: null tensor", who);
@@ -60,6 +61,7 @@ static bool tc_enabled() {
 }
 static int pick_impl(const coma_conv_args& a) {
   if (a.impl != COMA_IMPL_AUTO) return a.impl;
+  if (conv_simt_preferred(a)) return COMA_IMPL_SIMT;        // few-channel pointwise: HBM streaming kernel
   return (tc_enabled() && conv_tc_supported(a)) ? COMA_IMPL_TCGEN05 : COMA_IMPL_SIMT;
 }
 

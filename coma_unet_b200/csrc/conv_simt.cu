@@ -322,9 +322,133 @@ static int launch_pw1_t(const coma_conv_args& a, cudaStream_t stream) {
   return COMA_OK;
 }
 
-bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a); }
 
-int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : simt_chunks(a); }
+// ------------------------------------------------------------------------------------------------
+// Few-channel pointwise convolutions (the gate's W_g / W_x 1x1x1 convs in training mode and their data gradients, Cin, Cout <= 32):
+// 0.4 .. 0.8 GB of traffic and ~0.5 kFMA per voxel -- HBM streaming, not a GEMM.  On the 128-voxel-tile tcgen05 kernel they ran at
+// 15 % of the HBM peak (one K = 16/32 MMA per tile cannot hide the per-tile TMA / TMEM / epilogue round trip).  Here a thread
+// owns whole voxels: CIN values in registers, fp32 weights broadcast from shared memory, COUT accumulators, the same fused
+// prologue / epilogue (input affine + activation, bias, statistics partials, output affine + activation) as the other kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPwgThreads = 256, kPwgVox = 8;      // voxels per thread; a block (= one statistics chunk) covers 2048 voxels
+
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(kPwgThreads) conv_pwg_kernel(coma_conv_args a, int chunks) {
+  __shared__ __align__(16) float ws[CIN][COUT];
+  __shared__ float red[kPwgThreads / 32][COUT][2];
+  __shared__ float cb[COUT], cs[COUT], ch[COUT];      // bias, output scale / shift of this sample (defaults 0, 1, 0)
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const T* wb = static_cast<const T*>(a.w) + (int64_t)b * a.w_bstride;
+  for (int i = threadIdx.x; i < CIN * COUT; i += kPwgThreads) ws[i % CIN][i / CIN] = Elem<T>::ld(wb + i);     // w[co][ci] -> ws[ci][co]
+  __shared__ float isc[CIN], ish[CIN];               // input prologue coefficients (broadcast reads; registers go to the accumulators)
+  const bool pro = a.in_scale != nullptr;
+  const float ineg = a.in_act == COMA_ACT_NONE ? 1.f : (a.in_act == COMA_ACT_RELU ? 0.f : (a.in_slope ? __ldg(a.in_slope) : 0.f));
+  if (pro && threadIdx.x < CIN) {
+    isc[threadIdx.x] = __ldg(a.in_scale + (int64_t)b * CIN + threadIdx.x);
+    ish[threadIdx.x] = __ldg(a.in_shift + (int64_t)b * CIN + threadIdx.x);
+  }
+  if (threadIdx.x < COUT) {
+    cb[threadIdx.x] = a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride + threadIdx.x) : 0.f;
+    cs[threadIdx.x] = a.scale ? __ldg(a.scale + (int64_t)b * COUT + threadIdx.x) : 1.f;
+    ch[threadIdx.x] = a.scale ? __ldg(a.shift + (int64_t)b * COUT + threadIdx.x) : 0.f;
+  }
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  __syncthreads();
+  const T* xb = static_cast<const T*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co;
+  T* yb = static_cast<T*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co;
+  float s1[COUT], s2[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) s1[j] = s2[j] = 0.f;
+  const bool simple = a.act == COMA_ACT_NONE || a.act == COMA_ACT_RELU || a.act == COMA_ACT_LEAKY;      // act(u) = max(u, 0) + aneg * min(u, 0)
+  const float aneg = a.act == COMA_ACT_NONE ? 1.f : (a.act == COMA_ACT_RELU ? 0.f : slope);
+  const int64_t v0 = (int64_t)chunk * (kPwgThreads * kPwgVox);
+#pragma unroll 2
+  for (int it = 0; it < kPwgVox; ++it) {
+    const int64_t v = v0 + it * kPwgThreads + threadIdx.x;
+    if (v - (threadIdx.x & 31) >= Vo) break;                        // warp-uniform: the staged store below is warp-collective
+    const bool live = v < Vo;
+    float xv[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; c += 8) load8(xb + (live ? v : Vo - 1) * a.x_cs + c, *reinterpret_cast<float(*)[8]>(&xv[c]));
+    if (pro) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const float u = fmaf(isc[c], xv[c], ish[c]);
+        xv[c] = fmaf(ineg, fminf(u, 0.f), fmaxf(u, 0.f));
+      }
+    }
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int j = 0; j < COUT; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[c][j]);
+        acc[j] = fmaf(xv[c], w4.x, acc[j]);
+        acc[j + 1] = fmaf(xv[c], w4.y, acc[j + 1]);
+        acc[j + 2] = fmaf(xv[c], w4.z, acc[j + 2]);
+        acc[j + 3] = fmaf(xv[c], w4.w, acc[j + 3]);
+      }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+      const float val = live ? acc[j] + cb[j] : 0.f;
+      s1[j] += val;
+      s2[j] = fmaf(val, val, s2[j]);
+      const float u = fmaf(cs[j], val, ch[j]);
+      acc[j] = simple ? fmaf(aneg, fminf(u, 0.f), fmaxf(u, 0.f)) : act_fwd(a.act, u, slope);
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; j += 8)
+      if (live) store8(yb + v * a.y_cs + j, *reinterpret_cast<const float(*)[8]>(&acc[j]));
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+      const float t1 = warp_sum(s1[j]), t2 = warp_sum(s2[j]);
+      if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][j][0] = t1; red[threadIdx.x >> 5][j][1] = t2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < COUT * 2) {
+      const int j = threadIdx.x >> 1, q = threadIdx.x & 1;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPwgThreads / 32; ++w) t += red[w][j][q];
+      a.stats[(((int64_t)b * chunks + chunk) * COUT + j) * 2 + q] = t;
+    }
+  }
+}
+
+static bool pwg_applicable(const coma_conv_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_PWG"); return e && e[0] == '1'; }();
+  const int esz = a.dtype == COMA_BF16 ? 2 : 4;
+  const uintptr_t al = 8 * esz > 16 ? 16 : 8 * esz;
+  return !off && a.ksize == 1 && a.stride == 1 && !a.transposed && (a.Cin == 16 || a.Cin == 32) && a.Cout == 16 &&          // measured: 16 -> 32 is faster on the tcgen05 tile kernel (0.49 vs 0.78 ms)
+         a.y_cn == a.Cout && a.x_cs % 8 == 0 && a.x_co % 8 == 0 && a.y_cs % 8 == 0 && a.y_co % 8 == 0 &&
+         reinterpret_cast<uintptr_t>(a.x) % al == 0 && reinterpret_cast<uintptr_t>(a.y) % al == 0;
+}
+static int pwg_chunks(const coma_conv_args& a) {
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  return (int)((Vo + kPwgThreads * kPwgVox - 1) / (kPwgThreads * kPwgVox));
+}
+template <typename T>
+static int launch_pwg_t(const coma_conv_args& a, cudaStream_t stream) {
+  const int chunks = pwg_chunks(a);
+  dim3 grid((unsigned)chunks, (unsigned)a.B);
+  if (a.Cin == 16 && a.Cout == 16) conv_pwg_kernel<T, 16, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 32 && a.Cout == 16) conv_pwg_kernel<T, 32, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 16 && a.Cout == 32) conv_pwg_kernel<T, 16, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else conv_pwg_kernel<T, 32, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  COMA_CHECK_LAUNCH("conv_pwg");
+  return COMA_OK;
+}
+// the few-channel pointwise problems are HBM streaming: IMPL_AUTO prefers this kernel over the tcgen05 tile kernel (api.cu)
+bool conv_simt_preferred(const coma_conv_args& a) { return pwg_applicable(a); }
+
+bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a) || pwg_applicable(a); }
+
+int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : (pwg_applicable(a) ? pwg_chunks(a) : simt_chunks(a)); }
 
 int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
   if (pw_from1_applicable(a)) {
@@ -338,6 +462,7 @@ int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
     return COMA_OK;
   }
   if (pw1_applicable(a)) return a.dtype == COMA_BF16 ? launch_pw1_t<__nv_bfloat16>(a, stream) : launch_pw1_t<float>(a, stream);
+  if (pwg_applicable(a)) return a.dtype == COMA_BF16 ? launch_pwg_t<__nv_bfloat16>(a, stream) : launch_pwg_t<float>(a, stream);
   if (a.dtype == COMA_BF16) return launch_simt_t<__nv_bfloat16>(a, stream);
   return launch_simt_t<float>(a, stream);
 }
@@ -477,10 +602,12 @@ __global__ void __launch_bounds__(256) wgrad_cg1_kernel(coma_wgrad_args a, int64
 // dw[kd,kh,kw][c] += x[i][c] * g[i - k + 1]; the 72 partial sums are reduced per block and added atomically.
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_cg1_k3s1_kernel(coma_wgrad_args a, int64_t vchunk) {
+  // vchunk counts x LINES here: a block walks whole W lines, so the (b, d, h) decode and the validity of the three g lines
+  // are per line, not per voxel (64-bit div / mod per voxel made the sweep instruction-bound: 1.3 ms for 0.3 GB)
   const int kd = blockIdx.y;
   const int CV = a.Cx >> 3, cvec = threadIdx.x % CV, vlane = threadIdx.x / CV, lanes = 256 / CV;
-  const int64_t Vx = (int64_t)a.Dx * a.Hx * a.Wx, total = (int64_t)a.B * Vx;
-  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, total);
+  const int64_t lines = (int64_t)a.B * a.Dx * a.Hx;
+  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, lines);
   const T* gp = static_cast<const T*>(a.g) + a.g_co;
   const T* xp = static_cast<const T*>(a.x) + a.x_co + cvec * 8;
   float acc[9][8];
@@ -488,27 +615,35 @@ __global__ void __launch_bounds__(256) wgrad_cg1_k3s1_kernel(coma_wgrad_args a, 
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-  for (int64_t i = begin + vlane; i < end; i += lanes) {
-    const int64_t bb = i / Vx, rem = i - bb * Vx;
-    const int iw = (int)(rem % a.Wx), t2 = (int)(rem / a.Wx);
-    const int ih = t2 % a.Hx, id = t2 / a.Hx;
+  for (int64_t line = begin; line < end; ++line) {
+    const int ih = (int)(line % a.Hx);
+    const int64_t t2 = line / a.Hx;
+    const int id = (int)(t2 % a.Dx);
+    const int64_t bb = t2 / a.Dx;
     const int od = id - kd + 1;
     if (od < 0 || od >= a.Dg) continue;
-    float xv[8];
-    load8(xp + i * a.x_cs, xv);
+    const T* xline = xp + line * a.Wx * a.x_cs;
     const T* gplane = gp + ((bb * a.Dg + od) * a.Hg) * (int64_t)a.Wg * a.g_cs;
+    for (int iw = vlane; iw < a.Wx; iw += lanes) {
+      float xv[8];
+      load8(xline + (int64_t)iw * a.x_cs, xv);
+      float gv[9];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int oh = ih - kh + 1;
-      if (oh < 0 || oh >= a.Hg) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int oh = ih - kh + 1;
+        const bool hok = oh >= 0 && oh < a.Hg;
+        const T* grow = gplane + (int64_t)(hok ? oh : 0) * a.Wg * a.g_cs;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ow = iw - kw + 1;
-        if (ow < 0 || ow >= a.Wg) continue;
-        const float gv = Elem<T>::ld(gplane + ((int64_t)oh * a.Wg + ow) * a.g_cs);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[kh * 3 + kw][e] = fmaf(gv, xv[e], acc[kh * 3 + kw][e]);
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ow = iw - kw + 1;
+          const bool ok = hok && ow >= 0 && ow < a.Wg;
+          gv[kh * 3 + kw] = ok ? Elem<T>::ld(grow + (int64_t)ow * a.g_cs) : 0.f;
+        }
       }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(gv[t], xv[e], acc[t][e]);
     }
   }
   // reduce over the voxel lanes that share a channel vector: lanes with equal (threadIdx.x % CV); CV divides 32
@@ -535,9 +670,9 @@ int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
   if (a.Cg == 1 && a.ksize == 3 && a.stride == 1 && a.Cx % 8 == 0 && a.Cx <= 64 && 32 % (a.Cx / 8) == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
-    const int64_t totx = (int64_t)a.B * a.Dx * a.Hx * a.Wx;
-    int64_t want = (int64_t)num_sms() * 4 / 3;
-    int64_t vchunk = std::max<int64_t>((totx + want - 1) / want, 4096);
+    const int64_t totx = (int64_t)a.B * a.Dx * a.Hx;          // x lines: the kernel's work unit
+    int64_t want = (int64_t)num_sms() * 8 / 3;
+    int64_t vchunk = std::max<int64_t>((totx + want - 1) / want, 8);
     const int64_t nch = (totx + vchunk - 1) / vchunk;
     dim3 grid((unsigned)nch, 3);
     if (a.dtype == COMA_BF16) wgrad_cg1_k3s1_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, vchunk);

@@ -63,7 +63,7 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
         start_epoch = kwargs["start_epoch"]
         scheduler = kwargs.get("scheduler") or ReduceLROnPlateau(optimizer, "min", patience=5, factor=0.2)
     else:
-        optimizer = torch.optim.AdamW(model.parameters(), lr)
+        optimizer = torch.optim.AdamW(model.parameters(), lr, fused=next(model.parameters()).is_cuda)   # one multi-tensor kernel per step
         scheduler = ReduceLROnPlateau(optimizer, "min", patience=5)
     engine = DataParallelEngine(model) if dist.is_available() and dist.is_initialized() else DataParallelEngine(model, world_size=1)
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0

@@ -18,7 +18,7 @@ model = bench.build_model(dev)
 mri, tau, roi, covars, dicts = bench.make_batch(B, 1234, device=dev)
 model.train(True)
 crit = bench.build_criterion()
-opt = torch.optim.AdamW(model.parameters(), 1e-3)
+opt = torch.optim.AdamW(model.parameters(), 1e-3, fused=True)
 
 
 def step():
