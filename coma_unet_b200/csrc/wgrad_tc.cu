@@ -1,7 +1,10 @@
 // Weight gradient of the 3x3x3 stride-1 convolutions on the 5th-generation tensor cores (tcgen05 / TMEM, sm_100a):
 //     dw[kd,kh,kw][cg][cx] += sum_v g[v][cg] * x[v + (kd-1, kh-1, kw-1)][cx]
 // Replaces cuDNN wgrad behind loss.backward() (attn_unet_data_parallel.py:884) for the Conv3d layers whose channels are
-// multiples of 32 (ConvBlock convs and AttentionLayer.merge, :285-306 and MONAI's attentionunet).
+// multiples of 16 (ConvBlock convs, AttentionLayer.merge, the modulator stacks; :285-306,495-497 and MONAI's attentionunet).
+// The text below describes the 32-channel / 32-voxel-line instance; the kernel is a template over the channels per row of
+// either operand (32 -> 64B swizzle, 16 -> 32B swizzle with eight row-shifted chunks in M, three of them useful) and over the
+// line length (W % 32 == 0: 8 lines x 32 voxels per plane; W == 16: 16 lines x 16 voxels).
 //
 // GEMM view.  K = voxels.  Both operands are read straight out of the NDHWC activations, i.e. MN-major (a shared-memory
 // row = one voxel, 32 channels = 64 bytes, 64B swizzle as written by TMA): profiles/r01_probe_mn_major_operand.log shows

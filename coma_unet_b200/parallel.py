@@ -10,7 +10,7 @@ wrap sites commented out at validation.py:268-269) with what it would have meant
   buckets in reverse parameter order, flat buffers the ``.grad`` tensors alias -- no pack/unpack copies);
 * parameters that received no gradient on ANY rank keep ``grad = None`` (AdamW then skips them exactly as in the
   single-process reference: ``reweigh*``, ``modulator*``, unused prompts, projection heads 0-3; SURVEY hard part 5)
-  -- decided by one tiny MAX all-reduce of a used-bitmask;
+  -- decided by one tiny MAX all-reduce of a used-bitmask, host to host (gloo), so the step never waits for the GPU;
 * ``gather_rnc`` all-gathers the ``[B_local,512]`` features / ``[B_local,6]`` labels so ``RnCLoss`` ranks the global
   batch (criterions.py:623-642), with the matching backward.
 
@@ -77,6 +77,13 @@ class DataParallelEngine:
                 off += n
             self.flat.append(flat)
         self.fired = torch.zeros(len(self.params), dtype=torch.uint8)      # host-side, filled by hooks
+        # The used-parameter mask lives on the HOST (the hooks run when autograd executes a node, ahead of the GPU), so its MAX
+        # all-reduce goes over a gloo group: an NCCL all-reduce would force a device->host read at the end of backward, i.e. the
+        # host would wait for the whole step and the GPU would idle while the optimizer step and the next forward are enqueued.
+        self.host_group = None
+        if dist.is_initialized() and dist.get_backend(group) != "gloo":
+            ranks = dist.get_process_group_ranks(group) if group is not None else None
+            self.host_group = dist.new_group(ranks=ranks, backend="gloo")
         self.pending = [len(idxs) for idxs in self.buckets]
         self.launched = [False] * len(self.buckets)
         self.handles = []
@@ -127,14 +134,12 @@ class DataParallelEngine:
             return
         for b in range(len(self.buckets)):
             self._launch(b)
-        mask = self.fired.to(self.flat[0].device)
-        self.handles.append(dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
+        used = self.fired.clone()
+        dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.host_group if self.host_group is not None else self.group)
         for h in self.handles:
-            h.wait()
-        used = mask.cpu()
-        for i, p in enumerate(self.params):
-            if not used[i]:
-                p.grad = None
+            h.wait()                                  # stream-level wait: the host does not block
+        for i in (used == 0).nonzero().flatten().tolist():
+            self.params[i].grad = None
         self.attached = False
 
     def gather_rnc(self, features, labels):
