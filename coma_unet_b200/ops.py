@@ -10,6 +10,8 @@ outputs, BatchNorm folding) is done with torch ops.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional
@@ -190,11 +192,20 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
     return y, stats
 
 
+_CG1_SIMT = os.environ.get("COMA_CG1_SIMT", "0") == "1"     # A/B switch: keep one-channel weight gradients on the CUDA-core sweep
+
+
 def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad"):
     """dw[tap][Cg][Cx] = sum_o g[o] (x) x[o*stride + k - pad]  (conv geometry, fp32)."""
     g, x = as_vol(g), as_vol(x)
     B, Dg, Hg, Wg, Cg = g.shape
     _, Dx, Hx, Wx, Cx = x.shape
+    if (Cg == 1 and ksize == 3 and stride == 1 and g.dtype == torch.bfloat16 and Cx % 16 == 0 and not _CG1_SIMT
+            and ((Wg % 32 == 0 and Hg % 8 == 0) or (Wg == 16 and Hg % 16 == 0)) and Dg >= 4):
+        # one-channel gradient (the 16 -> 1 modulator heads): the CUDA-core sweep is latency-bound (1.1 ms for 0.3 GB at batch 4);
+        # zero-padded to one 16-channel row it runs on the tcgen05 weight-gradient kernel (0.1 ms pad + 0.3 ms)
+        g16 = torch.nn.functional.pad(g, (0, 15))
+        return wgrad_raw(g16, x, ksize=ksize, stride=stride, kind=kind)[:, :1, :].contiguous()
     dw = torch.zeros(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
     a = L.WgradArgs()
     a.g, a.x, a.dw = L.ptr(g), L.ptr(x), L.ptr(dw)
@@ -238,7 +249,11 @@ class ConvFn(torch.autograd.Function):
         cin_buf = x.shape[-1]
         cout_w = weight.shape[1] if cfg.transposed else weight.shape[0]
         cout_store = cfg.cout_store or cout_w
-        use_tc_pad = x.dtype == torch.bfloat16 and cin_buf % 16 == 0 and cfg.impl != L.IMPL_SIMT
+        # one-output pointwise convs (the gate's psi, ProjectionHead 0) stream on the conv_pw1 kernel: padded to 16 outputs for the
+        # tensor-core tile kernel they cost 0.85 ms instead of 0.1-0.17 ms at 128^3, batch 4
+        pw1 = (cfg.ksize == 1 and cfg.stride == 1 and not cfg.transposed and cout_w == 1 and cout_store == 1
+               and cin_buf in (1, 2, 3, 8, 16, 32, 64))
+        use_tc_pad = x.dtype == torch.bfloat16 and cin_buf % 16 == 0 and cfg.impl != L.IMPL_SIMT and not pw1
         cout_comp = max(_round_up(cout_w, 16) if use_tc_pad else cout_w, cout_store)
         wp = pack_weight(weight, cfg.transposed, cin_buf, cout_comp, x.dtype)
         y, stats = conv_raw(pro if pro is not None else x, wp, bias, ksize=cfg.ksize, stride=cfg.stride, transposed=cfg.transposed,

@@ -77,6 +77,7 @@ CONV_CASES = [
     (2, 32, 16, 5, 16, 32, 3, 1, False),    # mixed row widths
     (1, 16, 32, 4, 8, 64, 3, 1, False),
     (2, 32, 64, 16, 16, 16, 3, 1, False),   # 16-voxel lines (the 16^3 level): 16 lines x 16 voxels per plane
+    (2, 16, 1, 6, 16, 32, 3, 1, False),     # one-channel gradient padded to a 16-channel row for the tcgen05 weight gradient
 ]
 
 
