@@ -420,6 +420,121 @@ __global__ void __launch_bounds__(kPwgThreads) conv_pwg_kernel(coma_conv_args a,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same few-channel pointwise convolutions on the warp-level tensor-core path, for the plain cases (bf16, no output affine /
+// activation / input prologue: the gate's W_g / W_x convs before their BatchNorm, and their data gradients): the CUDA-core kernel
+// above is instruction-bound (0.5 kFMA per voxel), while as m16n8k16 tiles the whole problem is four to eight mma.sync per 16
+// voxels and the A fragments are plain 4-byte loads straight from the NDHWC rows (row = voxel, two consecutive channels per register)
+// -- no shared-memory staging at all; the weights sit in registers as B fragments.  HBM streaming is what is left.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_pw_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kPwgThreads) conv_pwm_kernel(coma_conv_args a, int chunks) {
+  constexpr int KS = CIN / 16, NT = COUT / 8, TILES = kPwgVox * 32 / 16;      // 16-voxel tiles per warp and chunk
+  __shared__ float red[kPwgThreads / 32][COUT][2];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(a.w) + (int64_t)b * a.w_bstride;
+  uint32_t bf[KS][NT][2];                       // B fragments: w[co = n0 + g][ci = k0 + 2t (+8)], two channels per register
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const __nv_bfloat16* wp = wb + (int64_t)(nt * 8 + g) * CIN + ks * 16 + 2 * t;
+      bf[ks][nt][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
+      bf[ks][nt][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+    }
+  float bias[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bias[nt][j] = a.bias ? __ldg(a.bias + (int64_t)b * a.bias_bstride + nt * 8 + 2 * t + j) : 0.f;
+  float s1[NT][2], s2[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co + 2 * t;
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co + 2 * t;
+  const int64_t w0 = (int64_t)chunk * (kPwgThreads * kPwgVox) + (int64_t)warp * (TILES * 16);
+#pragma unroll 2
+  for (int tile = 0; tile < TILES; ++tile) {
+    const int64_t v0 = w0 + tile * 16;
+    if (v0 >= Vo) break;
+    const int64_t r0 = v0 + g, r1 = v0 + g + 8;
+    const bool ok0 = r0 < Vo, ok1 = r1 < Vo;
+    const __nv_bfloat16* x0 = xb + (ok0 ? r0 : Vo - 1) * a.x_cs;
+    const __nv_bfloat16* x1 = xb + (ok1 ? r1 : Vo - 1) * a.x_cs;
+    uint32_t af[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      af[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(x0 + ks * 16));
+      af[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(x1 + ks * 16));
+      af[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(x0 + ks * 16 + 8));
+      af[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(x1 + ks * 16 + 8));
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) mma_pw_bf16(acc, af[ks], bf[ks][nt][0], bf[ks][nt][1]);
+      const float v00 = acc[0] + bias[nt][0], v01 = acc[1] + bias[nt][1], v10 = acc[2] + bias[nt][0], v11 = acc[3] + bias[nt][1];
+      if (ok0) {
+        s1[nt][0] += v00; s1[nt][1] += v01; s2[nt][0] = fmaf(v00, v00, s2[nt][0]); s2[nt][1] = fmaf(v01, v01, s2[nt][1]);
+        *reinterpret_cast<uint32_t*>(yb + r0 * a.y_cs + nt * 8) = pack_bf16x2(v00, v01);
+      }
+      if (ok1) {
+        s1[nt][0] += v10; s1[nt][1] += v11; s2[nt][0] = fmaf(v10, v10, s2[nt][0]); s2[nt][1] = fmaf(v11, v11, s2[nt][1]);
+        *reinterpret_cast<uint32_t*>(yb + r1 * a.y_cs + nt * 8) = pack_bf16x2(v10, v11);
+      }
+    }
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float u1 = s1[nt][j], u2 = s2[nt][j];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { u1 += __shfl_xor_sync(0xffffffffu, u1, o); u2 += __shfl_xor_sync(0xffffffffu, u2, o); }
+        if (g == 0) { red[warp][nt * 8 + 2 * t + j][0] = u1; red[warp][nt * 8 + 2 * t + j][1] = u2; }
+      }
+    __syncthreads();
+    if (threadIdx.x < COUT * 2) {
+      const int j = threadIdx.x >> 1, q = threadIdx.x & 1;
+      float u = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPwgThreads / 32; ++w) u += red[w][j][q];
+      a.stats[(((int64_t)b * chunks + chunk) * COUT + j) * 2 + q] = u;
+    }
+  }
+}
+
+static bool pwm_applicable(const coma_conv_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_PWM"); return e && e[0] == '1'; }();
+  return !off && a.dtype == COMA_BF16 && a.ksize == 1 && a.stride == 1 && !a.transposed && (a.Cin == 16 || a.Cin == 32) &&
+         (a.Cout == 16 || a.Cout == 32) && a.y_cn == a.Cout && !a.scale && !a.in_scale && a.act == COMA_ACT_NONE &&
+         a.x_cs % 2 == 0 && a.x_co % 2 == 0 && a.y_cs % 2 == 0 && a.y_co % 2 == 0 && a.w_bstride % 2 == 0 &&
+         reinterpret_cast<uintptr_t>(a.x) % 4 == 0 && reinterpret_cast<uintptr_t>(a.y) % 4 == 0 && reinterpret_cast<uintptr_t>(a.w) % 4 == 0;
+}
+static int launch_pwm(const coma_conv_args& a, cudaStream_t stream) {
+  const int64_t Vo = (int64_t)a.Do * a.Ho * a.Wo;
+  const int chunks = (int)((Vo + kPwgThreads * kPwgVox - 1) / (kPwgThreads * kPwgVox));
+  dim3 grid((unsigned)chunks, (unsigned)a.B);
+  if (a.Cin == 16 && a.Cout == 16) conv_pwm_kernel<16, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 32 && a.Cout == 16) conv_pwm_kernel<32, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 16 && a.Cout == 32) conv_pwm_kernel<16, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else conv_pwm_kernel<32, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  COMA_CHECK_LAUNCH("conv_pwm");
+  return COMA_OK;
+}
+
 static bool pwg_applicable(const coma_conv_args& a) {
   static const bool off = [] { const char* e = getenv("COMA_DISABLE_PWG"); return e && e[0] == '1'; }();
   const int esz = a.dtype == COMA_BF16 ? 2 : 4;
@@ -444,11 +559,11 @@ static int launch_pwg_t(const coma_conv_args& a, cudaStream_t stream) {
   return COMA_OK;
 }
 // the few-channel pointwise problems are HBM streaming: IMPL_AUTO prefers this kernel over the tcgen05 tile kernel (api.cu)
-bool conv_simt_preferred(const coma_conv_args& a) { return pwg_applicable(a); }
+bool conv_simt_preferred(const coma_conv_args& a) { return pwm_applicable(a) || pwg_applicable(a); }
 
-bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a) || pwg_applicable(a); }
+bool conv_simt_prologue_fused(const coma_conv_args& a) { return pw1_applicable(a) || pwg_applicable(a); }   // (pwm takes no prologue)
 
-int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : (pwg_applicable(a) ? pwg_chunks(a) : simt_chunks(a)); }
+int conv_simt_stat_chunks(const coma_conv_args& a) { return pw1_applicable(a) ? pw1_chunks(a) : ((pwm_applicable(a) || pwg_applicable(a)) ? pwg_chunks(a) : simt_chunks(a)); }
 
 int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
   if (pw_from1_applicable(a)) {
@@ -462,6 +577,7 @@ int conv_simt_launch(const coma_conv_args& a, cudaStream_t stream) {
     return COMA_OK;
   }
   if (pw1_applicable(a)) return a.dtype == COMA_BF16 ? launch_pw1_t<__nv_bfloat16>(a, stream) : launch_pw1_t<float>(a, stream);
+  if (pwm_applicable(a)) return launch_pwm(a, stream);
   if (pwg_applicable(a)) return a.dtype == COMA_BF16 ? launch_pwg_t<__nv_bfloat16>(a, stream) : launch_pwg_t<float>(a, stream);
   if (a.dtype == COMA_BF16) return launch_simt_t<__nv_bfloat16>(a, stream);
   return launch_simt_t<float>(a, stream);
