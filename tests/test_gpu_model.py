@@ -298,3 +298,26 @@ def test_c4_inference_volume_160x192x160_matches_oracle():
     mean_auto = float(np.abs(auto - want).mean() / np.abs(want).max())
     assert e_ours < max(3e-2, 1.5 * e_auto), (e_ours, e_auto)
     assert mean_ours < max(3e-3, 1.5 * mean_auto), (mean_ours, mean_auto)
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_unselected_prompt_keeps_no_gradient(where):
+    """A prompt no sample of the batch selects keeps ``grad = None`` (the reference only touches the prompt its ``.item()`` branch
+    picks, attn_unet_data_parallel.py:638-639), with the covariates on the host (flags known at once) and on the device
+    (flags read back asynchronously during forward and looked at in backward: no host wait inside the step)."""
+    case = {"channels": [16, 32, 64, 128, 256], "shape": [32, 32, 32], "batch": 2, "seed": 23}
+    m = build(case, torch.bfloat16)
+    mri, tau, roi, covars, dicts = batch(case)
+    for positive, (has_pos, has_neg) in ((1.0, (True, False)), (0.0, (False, True))):
+        cov = covars.clone()
+        cov[:, :, 0] = positive
+        cov = cov.to(DEV) if where == "device" else cov.cpu()
+        m.zero_grad(set_to_none=True)
+        m.train(True)
+        pred, projected, final_repr = m(mri, cov, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        zeros = torch.zeros(final_repr.size(), device=DEV)
+        loss, _, _, _ = criterion(cu)(pred, tau, roi, (final_repr, zeros, zeros), (projected[-1], cov[:, -1].float().to(DEV)))
+        loss.backward()
+        assert (m.pos_dynamic_prompt.grad is not None) == has_pos
+        assert (m.neg_dynamic_prompt.grad is not None) == has_neg
+        assert m.general_dynamic_prompt.grad is not None

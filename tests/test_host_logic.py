@@ -94,3 +94,20 @@ def test_synthetic_dataset_contract():
     batch = next(iter(DataLoader(ds, batch_size=2)))
     assert batch[0].shape == (2, 1, 16, 16, 16) and batch[3][1].shape == (2, 1, 6) and len(batch[4]) == 2
     assert set(ds.roi_predictions(0)) == set(common.roi_names())
+
+
+def test_prepare_geometry_follows_the_reference_padding_rules():
+    """Host integers of the GPU input preparation: numpy round-half-even output size (VolumeDataset.py:241-245), centred padding with
+    the odd voxel at the end, only the y axis cropped (data_util.py:814-828), no padding when the z extent already matches
+    (VolumeDataset.py:261-264)."""
+    from coma_unet_b200 import prepare_geometry
+    res, out, before, ratio = prepare_geometry((255, 256, 250), (1.0, 1.0, 1.0))
+    assert res == [128, 128, 125] and out == res and before == [0, 0, 0] and ratio == [2.0, 2.0, 2.0]   # round(127.5) = 128; z matches: x stays 125
+    res, out, before, _ = prepare_geometry((250, 256, 251), (1.0, 1.0, 1.0))
+    assert res == [125, 128, 126] and out == [128, 128, 128] and before == [1, 0, 1]                      # round(125.5) = 126; odd voxel at the end
+    res, out, before, _ = prepare_geometry((100, 300, 90), (1.0, 1.0, 1.0))
+    assert res == [50, 150, 45] and out == [128, 128, 128] and before == [39, 0, 41]                               # y cropped at its end
+    res, out, before, _ = prepare_geometry((256, 200, 200), (1.0, 1.0, 1.0))
+    assert res == [128, 100, 100] and out == res and before == [0, 0, 0]                                           # z matches: no transform
+    res, out, _, ratio = prepare_geometry((64, 64, 64), (1.0, 1.0, 1.0), resize=False, pad_dims=None)
+    assert res == [64, 64, 64] and out == res and ratio == [1.0, 1.0, 1.0]
