@@ -245,7 +245,7 @@ def kernel_profile(step_fn, n=2):
         if name in ("coma_conv3d_fprop", "coma_convT3d_fprop", "coma_conv3d_dgrad", "coma_convT3d_dgrad"):
             a = cargs[0]._obj
             flops = conv_flops_of_call(name, a)
-            tc = bool(_lib.lib().coma_conv3d_tcgen05_supported(cargs[0])) and a.impl != _lib.IMPL_SIMT
+            tc = _lib.lib().coma_conv3d_impl(cargs[0]) == _lib.IMPL_TCGEN05
             shape = (a.B, a.Cin, a.Cout, a.Do, a.ksize, a.stride, a.transposed)
         elif name in ("coma_gate_fwd", "coma_norm_film_act_fwd", "coma_gate_apply_fwd", "coma_roi_paint", "coma_pack2_fwd"):
             a = cargs[0]._obj
@@ -265,6 +265,7 @@ def kernel_profile(step_fn, n=2):
         elif name in ("coma_conv3d_wgrad", "coma_convT3d_wgrad"):
             a = cargs[0]._obj
             flops = 2.0 * a.B * a.Dg * a.Hg * a.Wg * a.ksize ** 3 * a.Cg * a.Cx
+            tc = bool(_lib.lib().coma_conv3d_wgrad_tcgen05_supported(cargs[0]))
             shape = (a.B, a.Cg, a.Cx, a.Dg, a.ksize, a.stride, 0)
         else:
             shape = ()

@@ -112,6 +112,8 @@ EXPORTS = {
     "coma_last_error": (C.c_char_p, []),
     "coma_conv3d_stat_chunks": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_tcgen05_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "coma_conv3d_impl": (C.c_int, [C.POINTER(ConvArgs)]),
+    "coma_conv3d_wgrad_tcgen05_supported": (C.c_int, [C.POINTER(WgradArgs)]),
     "coma_conv3d_prologue_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "coma_convT3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),

@@ -91,6 +91,10 @@ extern "C" int coma_conv3d_stat_chunks(const coma_conv_args* a) {
   return impl == COMA_IMPL_TCGEN05 ? conv_tc_stat_chunks(*a) : conv_simt_stat_chunks(*a);
 }
 extern "C" int coma_conv3d_tcgen05_supported(const coma_conv_args* a) { return a && conv_tc_supported(*a) ? 1 : 0; }
+extern "C" int coma_conv3d_impl(const coma_conv_args* a) { return a ? pick_impl(*a) : COMA_IMPL_SIMT; }
+extern "C" int coma_conv3d_wgrad_tcgen05_supported(const coma_wgrad_args* a) {
+  return a && a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a) ? 1 : 0;
+}
 extern "C" int coma_conv3d_prologue_supported(const coma_conv_args* a) {
   if (!a || a->transposed) return 0;
   const int impl = pick_impl(*a);

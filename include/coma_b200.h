@@ -88,6 +88,9 @@ typedef struct {
 int coma_conv3d_stat_chunks(const coma_conv_args* a);
 /* 1 if the tcgen05/TMA implicit-GEMM path can take this problem (bf16, channel multiples of 16, ...) */
 int coma_conv3d_tcgen05_supported(const coma_conv_args* a);
+/* the COMA_IMPL_* this problem actually runs on (what COMA_IMPL_AUTO resolves to: few-channel pointwise problems stream on the
+ * CUDA-core / mma.sync kernels even where the tcgen05 tile kernel could take them) */
+int coma_conv3d_impl(const coma_conv_args* a);
 /* 1 if a fused kernel (not the generic CUDA-core gather) applies the input prologue of this problem */
 int coma_conv3d_prologue_supported(const coma_conv_args* a);
 int coma_conv3d_fprop(const coma_conv_args* a, coma_stream_t stream);
@@ -112,6 +115,8 @@ typedef struct {
   int32_t dtype;
   int32_t impl;
 } coma_wgrad_args;
+/* 1 if the tcgen05 weight-gradient kernel takes this problem (bf16, k3 s1, channels multiples of 16, W % 32 == 0 or W == 16) */
+int coma_conv3d_wgrad_tcgen05_supported(const coma_wgrad_args* a);
 int coma_conv3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
 int coma_convT3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
 
