@@ -416,7 +416,7 @@ def run_ours(args):
             traffic, traffic_src = k0["dram_traffic_bytes"], "profiles/r01_ncu_conv_kernels_summary.json (dram read+write, one launch)"
     except (OSError, KeyError, IndexError, ValueError):
         pass
-    roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (conv_halo3 / conv_halo_s2 / convT_halo / conv_tc kernels, all launches of one step)",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (conv_halo3 / conv_pair / conv_halo_s2 / convT_halo / conv_tc kernels and, in training, wgrad_tc; all launches of one step)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"], "launches_per_step": tc_n,
                 "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / max(total_ms, 1e-9),
