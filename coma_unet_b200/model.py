@@ -286,6 +286,11 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
     def get_depth(self):
         return self.depth
 
+    def data_dependent_parameters(self):
+        """Parameters whose gradient exists only if the local batch selects them (:638-639): DataParallelEngine reduces them
+        after backward, in a fixed order, instead of from their hooks."""
+        return [self.pos_dynamic_prompt, self.neg_dynamic_prompt]
+
     # -- ROI lookup table: host dicts -> one small pinned upload, no per-ROI device work ---------------
     def _roi_lut(self, roi_pred_dicts, device):
         B = len(roi_pred_dicts)

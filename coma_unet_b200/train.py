@@ -3,15 +3,18 @@
 Same call shape and the same state: ``criterion.gen_loss.batch_reduction = None`` (:717), AdamW(lr) +
 ReduceLROnPlateau('min', patience=5) unless resuming (:729-737), one optimizer step per batch (:884-885),
 ``scheduler.step(epoch_loss / num_samples)`` per epoch (:921), the checkpoint dict
-``{epoch, model_state_dict, optimizer_state_dict, loss, scheduler_state_dict}`` written every epoch to
-``<save_path>/checkpoints/checkpoint_latest_epoch.pth`` plus a numbered copy every ``val_iter`` = 5 epochs (:943-955), and a
-validation pass every ``val_iter`` epochs (:957-963).
+``{epoch, model_state_dict, optimizer_state_dict, loss, scheduler_state_dict}`` (``loss`` = the last batch's loss tensor,
+as in the reference) written every epoch to ``<save_path>/checkpoints/checkpoint_latest_epoch.pth`` plus a numbered copy
+whenever ``epoch % checkpoint_iter == 0`` (epochs 0, 5, 10, ...; :943-955), and a validation pass whenever
+``epoch % val_iter == 0`` (:957-963).
 
 What is deliberately different: no host synchronisation inside the step loop.  The reference calls ``loss.item()`` and
 per-sample ``gen_loss[b].item()`` every batch (:892,901-910) and logs full-tensor norms (criterions.py:203-204); here the
 running sums live on the device and are read once per epoch.  ROI prediction dicts come from ``roi_pred_fn(paths)``
 (the reference reads lab-private JSON lookups, :708-710,809-810).  With ``torch.distributed`` initialised the step is
-data-parallel through ``DataParallelEngine`` (gradient SUM all-reduce overlapped with backward, global-batch RnC).
+data-parallel through ``DataParallelEngine`` (gradient SUM all-reduce overlapped with backward, global-batch RnC): the
+engine broadcasts rank 0's parameters and buffers when it is built, and the epoch loss sums / sample counts are summed over
+ranks before ``scheduler.step`` so that ReduceLROnPlateau takes the same decision on every replica.
 """
 from __future__ import annotations
 
@@ -56,6 +59,7 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
     device = torch.device("cuda", cuda_id)
     roi_pred_fn = kwargs["roi_pred_fn"]
     val_iter = kwargs.get("val_iter", 5)
+    checkpoint_iter = kwargs.get("checkpoint_iter", 5)
     criterion.gen_loss.batch_reduction = None
     start_epoch = 0
     if from_checkpoint:
@@ -92,15 +96,17 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
             loss_sum += loss.detach()
             gen_sum += gen_loss.detach().sum()
             num_samples += mri.shape[0]
-        epoch_loss = float(loss_sum)                    # the only host sync of the epoch
+        # the only host sync of the epoch; summed over ranks so every replica's scheduler sees the global-batch figures.  (With
+        # several ranks every rank's loss already contains the global RnC term; the generative part is rank-local.)
+        epoch_loss, epoch_gen, num_samples = engine.all_reduce_scalars(float(loss_sum), float(gen_sum), float(num_samples))
         scheduler.step(epoch_loss / max(num_samples, 1))
         history["epoch_avg_loss"].append(epoch_loss / max(num_samples, 1))
-        history["epoch_avg_gen_loss"].append(float(gen_sum) / max(num_samples, 1))
+        history["epoch_avg_gen_loss"].append(epoch_gen / max(num_samples, 1))
         if ckpt_dir and rank == 0:
             ckpt = {"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
-                    "loss": epoch_loss, "scheduler_state_dict": scheduler.state_dict()}
+                    "loss": loss.detach() if num_samples else None, "scheduler_state_dict": scheduler.state_dict()}
             torch.save(ckpt, os.path.join(ckpt_dir, "checkpoint_latest_epoch.pth"))
-            if (epoch + 1) % val_iter == 0:
+            if epoch % checkpoint_iter == 0:
                 torch.save(ckpt, os.path.join(ckpt_dir, f"checkpoint_epoch_{epoch}.pth"))
         if validation_loader is not None and (epoch % val_iter == 0 or epoch == epochs - 1):
             history["val_mae"].append((epoch, validate(model, validation_loader, roi_pred_fn, device)))

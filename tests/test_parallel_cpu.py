@@ -26,13 +26,16 @@ class Toy(nn.Module):
         prompt = torch.stack([self.pos if fl == 1 else self.neg for fl in flag.tolist()])
         return self.head(f * prompt), f
 
+    def data_dependent_parameters(self):
+        return [self.pos, self.neg]
 
-def make_data():
+
+def make_data(flags=(1, 1, 1, 1)):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(4, 6, generator=g)
     y = torch.randn(4, 1, generator=g)
     labels = torch.rand(4, 6, generator=g)
-    flag = torch.tensor([1, 1, 1, 1])    # no sample selects `neg` on any rank -> its grad must stay None
+    flag = torch.tensor(flags)    # (1,1,1,1): no sample selects `neg` on any rank -> its grad must stay None
     return x, y, labels, flag
 
 
@@ -40,57 +43,84 @@ def loss_fn(pred, y, feats, labels):
     return ((pred - y) ** 2).sum() + RnCLoss()(feats, labels)      # SUM over the batch + batch-coupled term
 
 
-def single_process():
+def single_process(flags=(1, 1, 1, 1)):
     torch.manual_seed(1)
     m = Toy()
-    x, y, labels, flag = make_data()
+    x, y, labels, flag = make_data(flags)
     pred, f = m(x, flag)
     loss_fn(pred, y, f, labels).backward()
     return {k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()}
 
 
-def worker(rank, world, port, out):
+def worker(rank, world, port, out, flags, bucket_mb, declare):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(1)
+    torch.manual_seed(1 + 7 * rank)                                       # replicas differ until the engine broadcasts rank 0's
     m = Toy()
-    eng = DataParallelEngine(m, world_size=world, bucket_mb=0.0005)      # tiny buckets -> several of them
+    eng = DataParallelEngine(m, world_size=world, bucket_mb=bucket_mb, late=None if declare else [])
     assert len(eng.buckets) > 2
-    x, y, labels, flag = make_data()
+    x, y, labels, flag = make_data(flags)
     sl = slice(rank * 2, rank * 2 + 2)
-    for step in range(2):                                                 # second step checks re-attachment
+    logs = []
+    for step in range(3):                                                 # later steps check re-attachment / rebuilt buckets
         for p in m.parameters():
             p.grad = None
         pred, f = m(x[sl], flag[sl])
         feats, lab = eng.gather_rnc(f, labels[sl])
         loss_fn(pred, y[sl], feats, lab).backward()
         eng.finish()
-    if rank == 0:
-        out.put({k: (None if p.grad is None else p.grad.tolist()) for k, p in m.named_parameters()})
+        logs.append([tuple(eng.buckets[b]) for b in eng.launch_log])      # the parameter sets reduced, in issue order
+    out.put((rank, {k: (None if p.grad is None else p.grad.tolist()) for k, p in m.named_parameters()}, logs,
+             eng.all_reduce_scalars(float(rank + 1), 2.0)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gradients_match_single_process():
+def run_two_ranks(flags, bucket_mb=0.0005, declare=True):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, out, flags, bucket_mb, declare)) for r in range(2)]
     for p in procs:
         p.start()
-    got = out.get()
+    got = dict((r, (g, logs, sc)) for r, g, logs, sc in (out.get(), out.get()))
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    want = single_process()
-    assert got["unused"] is None and want["unused"] is None
-    assert got["neg"] is None and want["neg"] is None
-    for k, g in want.items():
-        if g is not None:
-            assert torch.allclose(torch.tensor(got[k]), g, rtol=1e-5, atol=1e-6), k
+    return got
+
+
+def check_against_single_process(got, flags):
+    want = single_process(flags)
+    for rank in (0, 1):
+        grads = got[rank][0]
+        for k, g in want.items():
+            if g is None:
+                assert grads[k] is None, (rank, k)
+            else:
+                assert grads[k] is not None, (rank, k)
+                assert torch.allclose(torch.tensor(grads[k]), g, rtol=1e-5, atol=1e-6), (rank, k)
+    assert got[0][1] == got[1][1], "ranks issued their all-reduces in different orders"
+    assert got[0][2] == got[1][2] == [3.0, 4.0]
+
+
+def test_two_rank_gradients_match_single_process():
+    flags = (1, 1, 1, 1)
+    got = run_two_ranks(flags)
+    assert got[0][0]["unused"] is None and got[0][0]["neg"] is None
+    check_against_single_process(got, flags)
+
+
+def test_ranks_that_select_different_prompts_reduce_in_the_same_order():
+    """rank 0's samples select `pos`, rank 1's select `neg`; one parameter per bucket.  With launch-on-last-hook
+    the `pos` bucket of rank 0 was paired with the `neg` bucket of rank 1."""
+    flags = (1, 1, 0, 0)
+    check_against_single_process(run_two_ranks(flags, bucket_mb=1e-6), flags)
+    # an UNDECLARED data-dependent parameter only costs overlap (the cursor waits for finish()), never correctness
+    check_against_single_process(run_two_ranks(flags, bucket_mb=1e-6, declare=False), flags)
 
 
 def test_single_rank_engine_is_a_noop():
