@@ -208,7 +208,8 @@ class Convolution(nn.Module):
                 scale, shift = _pad_cols(scale, cout_comp, 1.0), _pad_cols(shift, cout_comp, 0.0)
             y, _ = ops.conv_raw(x, wp, conv.bias, ksize=self.kernel_size, stride=self.strides,
                                 transposed=self.is_transposed, cout_store=store, scale=scale, shift=shift,
-                                slope=None if slope is None else slope.detach(), act=code, out=out)
+                                slope=None if slope is None else slope.detach(), act=code, out=out,
+                                alg=(self.in_channels, self.out_channels))
             return y
         # --- general path: conv (+ statistics) then normalise / modulate / activate ------------------
         want_stats = mode in (L.NORM_INSTANCE, L.NORM_BATCH)

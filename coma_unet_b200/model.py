@@ -253,6 +253,9 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         self.depth = len(channels)
         ps = tuple(kwargs.get("prompt_shape", (128, 128, 128)))
         self.compute_dtype = kwargs.get("compute_dtype", torch.bfloat16)
+        # storage / compute dtype of the 1..16-channel modulator tail (deep_modulator_3c, fusion_layer, final_pred_head and the
+        # one-channel tensors between them); None = compute_dtype
+        self.tail_dtype = kwargs.get("tail_dtype", None)
 
         self.projection_heads = nn.ModuleList([
             ProjectionHead(channels[i], int((128 / 2 ** i) ** 3), latent_spaces[i]) for i in range(len(channels))])
@@ -309,6 +312,8 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
 
     def forward_modulator_with_uq(self, x, out, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
         """x: user input [B,1,D,H,W] fp32; out: backbone output NDHWC [B,D,H,W,1].  Returns NDHWC [B,D,H,W,1]."""
+        if self.tail_dtype is not None and out.dtype != self.tail_dtype:
+            out = out.to(self.tail_dtype)
         dev, dt = out.device, out.dtype
         B = x.shape[0]
         lut = self._roi_lut(roi_pred_dicts, dev)

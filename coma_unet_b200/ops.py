@@ -100,6 +100,21 @@ def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp:
     return p
 
 
+def invalidate_weight_caches(module: torch.nn.Module) -> None:
+    """Drop every cached packed weight / folded BatchNorm of ``module``.
+
+    The caches are keyed by the parameters' version counters, which in-place updates through ``.data`` (EMA swaps, manual
+    clipping on ``p.data``) do not bump: call this after such an update.  ``load_state_dict``, optimizers and ``copy_`` under
+    ``no_grad`` do bump the counter and need nothing."""
+    for p in module.parameters():
+        p.__dict__.pop("_coma_packed", None)
+    for m in module.modules():
+        if hasattr(m, "_fold_key"):
+            m._fold_key = None
+        if hasattr(m, "_fb"):
+            m._fb = None
+
+
 def _out_extent(n: int, k: int, stride: int, transposed: bool) -> int:
     if transposed:
         return n * stride
@@ -108,7 +123,7 @@ def _out_extent(n: int, k: int, stride: int, transposed: bool) -> int:
 
 
 def _conv_args(x, wp, bias, y, *, ksize, stride, transposed, cout_comp, scale=None, shift=None, slope=None, stats=None,
-               act=L.ACT_NONE, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0) -> L.ConvArgs:
+               act=L.ACT_NONE, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, alg=None) -> L.ConvArgs:
     B, Di, Hi, Wi, Cin = x.shape
     _, Do, Ho, Wo, ycn = y.shape
     a = L.ConvArgs()
@@ -120,6 +135,9 @@ def _conv_args(x, wp, bias, y, *, ksize, stride, transposed, cout_comp, scale=No
     a.ksize, a.stride, a.pad, a.transposed = ksize, stride, (ksize - 1) // 2, int(transposed)
     a.w_bstride, a.bias_bstride = w_bstride, bias_bstride
     a.act, a.dtype, a.impl = act, L.dtype_code(x.dtype), impl
+    # (Cin, Cout) of the LAYER, without the zero padding the tensor-core kernels compute on: bench.py counts algorithmic FLOPs
+    # from these (a Python attribute of the ctypes object, not part of the C struct)
+    a.alg = alg if alg is not None else (Cin, cout_comp)
     return a
 
 
@@ -157,7 +175,7 @@ def materialized(x):
 
 
 def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None, scale=None, shift=None, slope=None,
-             act=L.ACT_NONE, want_stats=False, out=None, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, kind=None):
+             act=L.ACT_NONE, want_stats=False, out=None, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, kind=None, alg=None):
     """One conv kernel launch on packed weights.  Returns (y, stats_partial or None).  ``x`` may be a Deferred."""
     pro = x if isinstance(x, Deferred) else None
     x = as_vol(pro.raw if pro is not None else x)
@@ -175,7 +193,7 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
         bias = pb
     a = _conv_args(x, wp, None if bias is None else bias.float().contiguous(), y, ksize=ksize, stride=stride,
                    transposed=transposed, cout_comp=cout_comp, scale=scale, shift=shift, slope=slope, act=act, impl=impl,
-                   w_bstride=w_bstride, bias_bstride=bias_bstride)
+                   w_bstride=w_bstride, bias_bstride=bias_bstride, alg=alg)
     if pro is not None:
         a.in_scale, a.in_shift, a.in_slope, a.in_act = L.ptr(pro.A), L.ptr(pro.S), L.ptr(pro.slope), pro.act
         if pro.act not in (L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY) or not L.lib().coma_conv3d_prologue_supported(C.byref(a)):
@@ -195,7 +213,7 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
 _CG1_SIMT = os.environ.get("COMA_CG1_SIMT", "0") == "1"     # A/B switch: keep one-channel weight gradients on the CUDA-core sweep
 
 
-def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad"):
+def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad", alg=None):
     """dw[tap][Cg][Cx] = sum_o g[o] (x) x[o*stride + k - pad]  (conv geometry, fp32)."""
     g, x = as_vol(g), as_vol(x)
     B, Dg, Hg, Wg, Cg = g.shape
@@ -205,13 +223,14 @@ def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad"):
         # one-channel gradient (the 16 -> 1 modulator heads): the CUDA-core sweep is latency-bound (1.1 ms for 0.3 GB at batch 4);
         # zero-padded to one 16-channel row it runs on the tcgen05 weight-gradient kernel (0.1 ms pad + 0.3 ms)
         g16 = torch.nn.functional.pad(g, (0, 15))
-        return wgrad_raw(g16, x, ksize=ksize, stride=stride, kind=kind)[:, :1, :].contiguous()
+        return wgrad_raw(g16, x, ksize=ksize, stride=stride, kind=kind, alg=alg or (1, Cx))[:, :1, :].contiguous()
     dw = torch.zeros(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
     a = L.WgradArgs()
     a.g, a.x, a.dw = L.ptr(g), L.ptr(x), L.ptr(dw)
     a.B, a.Dg, a.Hg, a.Wg, a.Dx, a.Hx, a.Wx = B, Dg, Hg, Wg, Dx, Hx, Wx
     a.Cg, a.Cx, a.g_cs, a.g_co, a.x_cs, a.x_co = Cg, Cx, vol_cs(g), 0, vol_cs(x), 0
     a.ksize, a.stride, a.pad, a.dtype, a.impl = ksize, stride, (ksize - 1) // 2, L.dtype_code(g.dtype), L.IMPL_AUTO
+    a.alg = alg if alg is not None else (Cg, Cx)       # layer channel counts without padding (see _conv_args)
     L.call(kind, C.byref(a), L.stream())
     return dw
 
@@ -256,8 +275,9 @@ class ConvFn(torch.autograd.Function):
         use_tc_pad = x.dtype == torch.bfloat16 and cin_buf % 16 == 0 and cfg.impl != L.IMPL_SIMT and not pw1
         cout_comp = max(_round_up(cout_w, 16) if use_tc_pad else cout_w, cout_store)
         wp = pack_weight(weight, cfg.transposed, cin_buf, cout_comp, x.dtype)
+        cin_w = weight.shape[0] if cfg.transposed else weight.shape[1]
         y, stats = conv_raw(pro if pro is not None else x, wp, bias, ksize=cfg.ksize, stride=cfg.stride, transposed=cfg.transposed,
-                            cout_store=cout_store, want_stats=cfg.want_stats, impl=cfg.impl)
+                            cout_store=cout_store, want_stats=cfg.want_stats, impl=cfg.impl, alg=(cin_w, cout_w))
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cout_comp, ctx.has_bias = cfg, cout_comp, bias is not None
         if stats is None:
@@ -273,29 +293,28 @@ class ConvFn(torch.autograd.Function):
         cin_buf, cout_store = x.shape[-1], dy.shape[-1]
         k = cfg.ksize
         dx = dw = db = None
+        cin_w, cout_w = (weight.shape[0], weight.shape[1]) if cfg.transposed else (weight.shape[1], weight.shape[0])
         if ctx.needs_input_grad[0]:
             wp = pack_weight(weight, cfg.transposed, cin_buf, ctx.cout_comp, x.dtype)[:, :cout_store, :]
+            alg = (cout_w, cin_w)
             if cfg.transposed:      # adjoint of convT(stride s) = conv(stride s), channels swapped
                 adj = wp.transpose(1, 2).contiguous()
-                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=False, kind="coma_convT3d_dgrad")
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=False, kind="coma_convT3d_dgrad", alg=alg)
             elif cfg.stride == 1:   # adjoint of conv(stride 1) = conv with flipped taps, channels swapped
                 adj = wp.flip(0).transpose(1, 2).contiguous()
-                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=1, transposed=False, kind="coma_conv3d_dgrad")
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=1, transposed=False, kind="coma_conv3d_dgrad", alg=alg)
             else:                   # adjoint of conv(stride s) = convT(stride s)
                 adj = wp.transpose(1, 2).contiguous()
-                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=True, kind="coma_conv3d_dgrad")
+                dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=True, kind="coma_conv3d_dgrad", alg=alg)
             assert dx.shape == x.shape, (dx.shape, x.shape)
         if ctx.needs_input_grad[1]:
             if cfg.transposed:
-                cin_w, cout_w = weight.shape[0], weight.shape[1]
-                dwp = wgrad_raw(x, dy, ksize=k, stride=cfg.stride, kind="coma_convT3d_wgrad")   # [T, cin_buf, cout_store]
+                dwp = wgrad_raw(x, dy, ksize=k, stride=cfg.stride, kind="coma_convT3d_wgrad", alg=(cin_w, cout_w))   # [T, cin_buf, cout_store]
                 dw = dwp[:, :cin_w, :cout_w].reshape(k, k, k, cin_w, cout_w).permute(3, 4, 0, 1, 2).contiguous()
             else:
-                cout_w, cin_w = weight.shape[0], weight.shape[1]
-                dwp = wgrad_raw(dy, x, ksize=k, stride=cfg.stride)                               # [T, cout_store, cin_buf]
+                dwp = wgrad_raw(dy, x, ksize=k, stride=cfg.stride, alg=(cout_w, cin_w))           # [T, cout_store, cin_buf]
                 dw = dwp[:, :cout_w, :cin_w].reshape(k, k, k, cout_w, cin_w).permute(3, 4, 0, 1, 2).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            cout_w = weight.shape[1] if cfg.transposed else weight.shape[0]
             if cfg.bias_grad_zero:
                 db = torch.zeros(cout_w, device=x.device, dtype=torch.float32)
             else:

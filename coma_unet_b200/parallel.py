@@ -63,6 +63,9 @@ class DataParallelEngine:
         self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.enabled = self.world > 1
         self.comm_bytes = 0          # gradient bytes all-reduced in the last step (bench.py reports it)
+        self.timing = False          # bench.py: CUDA events around the wait for the all-reduce tail (exposed communication)
+        self.timing_events = []
+        self.launched_in_backward = 0
         if not self.enabled:
             return
         if broadcast:                # replicas start from rank 0's state, as DistributedDataParallel does
@@ -179,6 +182,7 @@ class DataParallelEngine:
         some rank used (in index order), wait."""
         if not self.enabled:
             return
+        self.launched_in_backward = len(self.launch_log)
         for b in range(self.n_early):
             self._launch(b)
         self.cursor = self.n_early
@@ -187,8 +191,14 @@ class DataParallelEngine:
         for b in range(self.n_early, len(self.buckets)):
             if any(used[i] for i in self.buckets[b]):     # identical on every rank: ``used`` is the global mask
                 self._launch(b)
+        if self.timing:    # the compute stream idles between these two events exactly as long as the all-reduce tail is exposed
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for h in self.handles:
             h.wait()                                  # stream-level wait: the host does not block
+        if self.timing:
+            e1.record()
+            self.timing_events.append((e0, e1))
         for i in (used == 0).nonzero().flatten().tolist():
             self.params[i].grad = None
         self.attached = False
