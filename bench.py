@@ -474,7 +474,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
         e0, e1 = timed_steps(2)                   # the last two warm-up steps calibrate the length of the timed window
         torch.cuda.synchronize()
         est_ms = max_over_ranks(e0.elapsed_time(e1) / 2.0, world, device)
-        steps = max(args.steps, int(math.ceil(args.min_seconds * 1000.0 / max(est_ms, 1e-3))))
+        steps = max(args.steps, int(math.ceil(1.08 * args.min_seconds * 1000.0 / max(est_ms, 1e-3))))
         barrier(world)
         torch.cuda.synchronize()
         l0 = _lib.launches

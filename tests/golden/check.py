@@ -17,6 +17,14 @@ def load():
     return data, meta
 
 
+def load2():
+    """Round-2 fixtures (tests/golden/make_golden2.py): train64, eval128_full."""
+    data = np.load(os.path.join(HERE, "golden2.npz"))
+    with open(os.path.join(HERE, "golden2_meta.json")) as f:
+        meta = json.load(f)
+    return data, meta
+
+
 def rel_err(a: np.ndarray, b: np.ndarray, floor_frac: float = 1e-3) -> float:
     """Per-voxel relative error max |a-b| / max(|b|, floor_frac*max|b|)  (SURVEY.md section 7 hard part 7)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

@@ -21,6 +21,7 @@ from oracle import model as omodel         # noqa: E402
 from tests.golden import check, common     # noqa: E402
 
 DATA, META = check.load()
+DATA2, META2 = check.load2()
 DEV = "cuda"
 
 
@@ -82,6 +83,100 @@ def test_fp32_train_step_matches_reference_fixture(name):
     with torch.no_grad():
         pred_eval = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
     assert fp32_close(*check.sampled(DATA, f"{name}/pred_eval", pred_eval))
+
+
+def test_fp32_train64_gradients_match_reference_fixture():
+    """Round-2 fixture (64^3, batch 2, the reference's own code): with 2 x 4^3 voxels per BatchNorm channel at the bottom level
+    the fp32 gradients are well-conditioned and the CUDA path is held to 1e-3 of each gradient's full scale."""
+    name, case = "train64", META2["train64"]
+    m = build(case, torch.float32)
+    mri, tau, roi, covars, dicts = batch(case)
+    m.train(True)
+    pred, projected, final_repr = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    zeros = torch.zeros(final_repr.size(), device=DEV)
+    loss, gen, ps, ds = criterion(cu)(pred, tau, roi, (final_repr, zeros, zeros), (projected[-1], covars[:, -1].float().to(DEV)))
+    loss.backward()
+    assert fp32_close(*check.sampled(DATA2, f"{name}/pred", pred))
+    assert check.rel_err([float(loss.detach()), float(ps), float(ds)], DATA2[f"{name}/loss"]) < 1e-4
+    params = dict(m.named_parameters())
+    assert sorted(k for k, p in params.items() if p.grad is None) == case["no_grad_params"]
+    worst = {}
+    for k in sorted({k.split("/grad/")[1].rsplit("/", 1)[0] for k in DATA2.files if k.startswith(f"{name}/grad/")}):
+        got, want = check.sampled(DATA2, f"{name}/grad/{k}", params[k].grad)
+        if abs(want).max() < 1e-6:
+            assert abs(got).max() < 1e-6, k
+            continue
+        worst[k] = check.scaled_err(got, want)
+    assert max(worst.values()) < 1e-3, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+# bf16 error model (profiles/r02_error_trace_*.log): every layer adds ~2.4e-3 rms of relative error (bf16 rounding of its
+# operands and of its stored output); over the ~36 layers between input and prediction these add in quadrature.
+BF16_LAYER_RMS, BF16_DEPTH = 2.4e-3, 36
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_eval128_full_width_matches_reference_fixture(dtype):
+    """The BENCHMARKED configuration (128^3, channels [32..512]) against the reference's own forward (golden2.npz)."""
+    case = META2["eval128_full"]
+    m = build(case, dtype).eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = batch(case)
+    with torch.no_grad():
+        pred = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    got, want = check.sampled(DATA2, "eval128_full/pred_eval", pred)
+    if dtype == torch.float32:
+        assert fp32_close(got, want)
+        return
+    rms = float(np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()))
+    mx = check.scaled_err(got, want)
+    print(f"eval128_full bf16: rms rel {rms:.3e}, max scaled {mx:.3e}")
+    # accumulated rounding of ~36 bf16 layers, 1.5x margin; the worst of 32768 sampled voxels within 6 sigma of it
+    assert rms < 1.5 * BF16_LAYER_RMS * BF16_DEPTH ** 0.5, rms
+    assert mx < 6 * 1.5 * BF16_LAYER_RMS * BF16_DEPTH ** 0.5, mx
+
+
+def test_bf16_train_step_128_full_width_tracks_fp32_oracle():
+    """A training step on the configuration the training number is quoted on -- 128^3, channels [32..512], bf16, batch 2 --
+    against the fp32 oracle on the same GPU (cuDNN fp32, TF32 off): prediction, loss, and EVERY probed gradient by scaled
+    error max|a-b| / max|b|.  The bounds are the bf16 error model above (forward) and twice its depth for the
+    gradients (forward + backward chain); measured values are printed."""
+    from tests.golden.make_golden import PROBE_PARAMS
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    case = {"channels": [32, 64, 128, 256, 512], "shape": [128, 128, 128], "batch": 2, "seed": 33}
+    mri, tau, roi, covars, dicts = batch(case)
+    covars[0, 0, 0], covars[1, 0, 0] = 1.0, 0.0          # one positive and one negative sample: both prompts get a gradient
+    outs = []
+    for cls, mod, dtype in ((lambda *a, compute_dtype=None, **k: omodel.ContrastiveAttentionUNET_DP(*a, **k), ocrit, None),
+                            (cu.ContrastiveAttentionUNET_DP, cu, torch.bfloat16)):
+        model = build(case, dtype, cls=cls)
+        model.train(True)
+        pred, projected, final_repr = model(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        zeros = torch.zeros(final_repr.size(), device=DEV)
+        loss, gen, _, _ = criterion(mod)(pred, tau, roi, (final_repr, zeros, zeros), (projected[-1], covars[:, -1].float().to(DEV)))
+        loss.backward()
+        grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+        outs.append((pred.detach().float().cpu(), float(loss.detach()), grads))
+        del model, pred, projected, final_repr, loss, gen
+        torch.cuda.empty_cache()
+    (po, lo, go), (pm, lm, gm) = outs
+    assert set(go) == set(gm)
+    fwd_rms = float((pm - po).pow(2).mean().sqrt() / po.pow(2).mean().sqrt())
+    fwd_max = check.scaled_err(pm.numpy(), po.numpy())
+    report = {"pred_rms": fwd_rms, "pred_max": fwd_max, "loss_rel": abs(lm - lo) / abs(lo)}
+    bound_rms = 1.5 * BF16_LAYER_RMS * BF16_DEPTH ** 0.5
+    assert fwd_rms < bound_rms and fwd_max < 6 * bound_rms and abs(lm - lo) < bound_rms * abs(lo), report
+    worst = {}
+    for k in PROBE_PARAMS:
+        if k not in go or float(go[k].abs().max()) < 1e-12:
+            continue
+        a, b = gm[k].double(), go[k].double()
+        worst[k] = (float((a - b).abs().max() / b.abs().max()), float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()))
+    print("bf16 train step 128^3 full width:", report, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in worst.items()})
+    grad_rms_bound = 1.5 * BF16_LAYER_RMS * (2 * BF16_DEPTH) ** 0.5
+    bad = {k: v for k, v in worst.items() if v[1] > 2 * grad_rms_bound or v[0] > 6 * 2 * grad_rms_bound}
+    assert not bad, bad
 
 
 def fp32_close(got, want):

@@ -545,6 +545,46 @@ def test_full_size_stride2_and_transposed_round_trip_shapes_and_adjointness():
     assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0) + 2e-3 * float(y.float().norm() * g.float().norm()) * 1e-2
 
 
+FULL_NUMERIC = [
+    # (B, Cin, Cout, D, k, stride, transposed): the layers of the benchmarked network at batch 8
+    (8, 64, 32, 128, 3, 1, False),     # merge conv of the top level (CTA-pair kernel)
+    (8, 32, 32, 128, 3, 1, False),     # head conv 2 (plane-ring kernel)
+    (8, 16, 16, 128, 3, 1, False),     # modulator stack conv
+    (8, 32, 64, 128, 3, 2, False),     # first down-sampling conv (stride-2 plane ring)
+    (8, 64, 32, 64, 3, 2, True),       # top-level transposed conv
+    (8, 128, 64, 64, 3, 1, False),     # second-level merge conv (CTA pair, two K chunks)
+]
+
+
+@pytest.mark.parametrize("case", FULL_NUMERIC)
+def test_full_size_tcgen05_conv_matches_cudnn_fp32(case):
+    """The tcgen05 kernels at the BENCHMARK size, numerically: forward, data gradient and weight gradient against
+    F.conv3d / F.conv_transpose3d in fp32 (TF32 off) on the same bf16-representable inputs.  Only accumulation order and
+    the bf16 rounding of the stored result differ, so the bound is bf16's 2^-8 of full scale for tensors stored in bf16
+    and 1e-3 for the fp32 weight gradient (1.7e7 voxels x 8 samples of fp32 accumulation, atomically combined)."""
+    B, Cin, Cout, D, k, s, tr = case
+    Di = D
+    g = torch.Generator(device=DEV).manual_seed(90)
+    x = torch.randn(B, Cin, Di, Di, Di, device=DEV, generator=g).bfloat16().float()
+    wshape = (Cin, Cout, k, k, k) if tr else (Cout, Cin, k, k, k)
+    w = (torch.randn(*wshape, device=DEV, generator=g) * (Cin * k ** 3) ** -0.5).bfloat16().float()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    pad = (k - 1) // 2
+    ref = F.conv_transpose3d(xr, wr, None, stride=s, padding=pad, output_padding=s - 1) if tr else F.conv3d(xr, wr, None, stride=s, padding=pad)
+    gy = torch.randn(ref.shape, device=DEV, generator=g).bfloat16().float()
+    ref.backward(gy)
+    ref = ref.detach()
+    xv = x.permute(0, 2, 3, 4, 1).contiguous().bfloat16().requires_grad_(True)
+    del x
+    wp = w.clone().requires_grad_(True)
+    y, _ = ops.conv3d(xv, wp, None, ops.ConvCfg(ksize=k, stride=s, transposed=tr))
+    assert err(y.permute(0, 4, 1, 2, 3), ref) < 2 ** -8
+    del ref
+    y.backward(gy.permute(0, 2, 3, 4, 1).contiguous().bfloat16())
+    assert err(xv.grad.permute(0, 4, 1, 2, 3), xr.grad) < 2 ** -8
+    assert err(wp.grad, wr.grad) < 1e-3
+
+
 @pytest.mark.parametrize("case", [(8, 128, 64, 64, 3, 1, False), (8, 64, 32, 128, 3, 1, False), (8, 16, 16, 128, 3, 1, False),
                                   (8, 32, 64, 128, 3, 2, False), (8, 64, 32, 64, 3, 2, True)])
 def test_warp_specialised_convs_are_run_to_run_identical(case):

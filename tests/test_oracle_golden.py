@@ -12,6 +12,7 @@ from oracle import model as omodel
 from tests.golden import check, common
 
 DATA, META = check.load()
+DATA2, META2 = check.load2()
 TOL = 1e-4
 
 
@@ -60,8 +61,36 @@ def test_train_step_matches_reference(name):
     assert check.rel_err(*check.sampled(DATA, f"{name}/pred_eval", pred_eval)) < TOL
 
 
-def make_probe_list(name):
-    return sorted({k.split("/grad/")[1].rsplit("/", 1)[0] for k in DATA.files if k.startswith(f"{name}/grad/")})
+def make_probe_list(name, data=DATA):
+    return sorted({k.split("/grad/")[1].rsplit("/", 1)[0] for k in data.files if k.startswith(f"{name}/grad/")})
+
+
+def test_train64_matches_reference():
+    """Round-2 fixture: 64^3, batch 2 -- well-conditioned BatchNorm at the bottom level, gradients held to 1e-4."""
+    name, case = "train64", META2["train64"]
+    m = build(case)
+    mri, tau, roi, covars, dicts = common.synthetic_batch(case["batch"], case["shape"], case["seed"])
+    m.train(True)
+    pred, projected, final_repr = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    zeros = torch.zeros(final_repr.size())
+    loss, gen, ps, ds = criterion()(pred, tau, roi, (final_repr, zeros, zeros), (projected[-1], covars[:, -1].float()))
+    loss.backward()
+    assert check.rel_err(*check.sampled(DATA2, f"{name}/pred", pred)) < TOL
+    assert check.rel_err([float(loss.detach()), float(ps), float(ds)], DATA2[f"{name}/loss"]) < TOL
+    params = dict(m.named_parameters())
+    assert sorted(k for k, p in params.items() if p.grad is None) == case["no_grad_params"]
+    for k in make_probe_list(name, DATA2):
+        assert check.scaled_err(*check.sampled(DATA2, f"{name}/grad/{k}", params[k].grad)) < 1e-4, k
+
+
+def test_eval128_full_width_matches_reference():
+    case = META2["eval128_full"]
+    m = build(case).eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = common.synthetic_batch(case["batch"], case["shape"], case["seed"])
+    with torch.no_grad():
+        pred = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    assert check.rel_err(*check.sampled(DATA2, "eval128_full/pred_eval", pred)) < TOL
 
 
 def test_eval128_matches_reference():
