@@ -41,7 +41,7 @@ FILM_HIDDEN = 64
 
 def covariate_matrix(covariate, like: torch.Tensor) -> torch.Tensor:
     """``[B,1,n]`` (float32 or float64, VolumeDataset_ADNI_A4_combined.py:86) -> ``[B,n]`` in x's dtype."""
-    return covariate.reshape(covariate.shape[0], -1).to(device=like.device, dtype=torch.float32)
+    return covariate.reshape(covariate.shape[0], -1).to(device=like.device, dtype=like.dtype if like.is_floating_point() else torch.float32)
 
 
 class ExpertConv3d(nn.Module):

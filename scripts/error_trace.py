@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--width", type=int, default=32)
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--train", action="store_true", help="train-mode forward (BatchNorm batch statistics) instead of eval")
     ap.add_argument("--out", default="gpurun_out/error_trace.json")
     args = ap.parse_args()
     shape = tuple(args.shape * 3 if len(args.shape) == 1 else args.shape)
@@ -88,9 +89,10 @@ def main():
     mri, roi = mri.to(dev), roi.to(dev)
 
     def run(m):
-        m.eval()
-        m.set_training(False)
-        return m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        m.train(args.train)
+        m.set_training(args.train)
+        out = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        return out[0] if isinstance(out, (tuple, list)) else out
 
     oracle = common.fill_deterministic(omodel.ContrastiveAttentionUNET_DP(3, 1, 1, channels, [2] * 5, **kw), args.seed).to(dev)
     ref, order = capture(oracle, False, run)

@@ -6,6 +6,12 @@ run in the build container) but kept in their own file so that golden.npz stays 
                      have 2 x 2^3 there, which is why tests/test_gpu_model.py allows them 1e-2);
 * ``eval128_full`` -- an eval forward at 128^3 with the FULL channel widths [32..512] (the benchmarked configuration).
 
+* ``train64_fp64`` -- the same train step evaluated by the ORACLE in float64 (the oracle is pinned to the reference at 1e-4 by
+                     tests/test_oracle_golden.py), plus, per probed parameter, how far the reference's own float32 CPU result is
+                     from it (``fp32dev``).  float32 summation alone moves these gradients by up to 3e-3 (4e-2 for the prompt
+                     gradients, which are sums of a few huge cancelling terms), so the CUDA fp32 path is judged against the
+                     float64 values with the reference's own float32 deviation as the yardstick.
+
     python -m tests.golden.make_golden2            # from the repo root
 """
 from __future__ import annotations
@@ -21,11 +27,47 @@ from tests.golden import make_golden as mg
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def oracle_fp64_case(name, ref_name, channels, shape, batch, seed, out, meta):
+    """Oracle train step in float64; gradients sampled like train_case does + the float32 fixture's deviation from them."""
+    import torch.nn as nn
+    from oracle import criterions as ocrit
+    from oracle import model as omodel
+    from tests.golden import common
+    m = omodel.ContrastiveAttentionUNET_DP(3, 1, 1, channels, [2] * 5, latent_spaces=[2048] * 5, conditional=True,
+                                           prompt_shape=tuple(shape))
+    m.set_save_attn(None)
+    common.fill_deterministic(m, seed)
+    m = m.double()
+    mri, tau, roi, covars, dicts = common.synthetic_batch(batch, shape, seed)
+    gen = ocrit.RoiMSE(torch.tensor([225.0] * 36), common.ROI_INDICES, voxel_wise=False)
+    crit = ocrit.GenerativeContrastiveLoss(ocrit.RnCLoss(), gen, nn.TripletMarginLoss(1), 0., 1.)
+    crit.gen_loss.batch_reduction = None
+    m.train(True)
+    pred, projected, final_repr = m(mri.double(), covars.double(), roi_pred_dicts=dicts, sample_roi_mask=roi.double())
+    zeros = torch.zeros(final_repr.size(), dtype=torch.float64)
+    loss, _, _, _ = crit(pred, tau.double(), roi.double(), (final_repr, zeros, zeros), (projected[-1], covars[:, -1].double()))
+    loss.backward()
+    out[f"{name}/loss"] = np.array([float(loss.detach())])
+    params = dict(m.named_parameters())
+    dev = {}
+    for k in mg.PROBE_PARAMS:
+        if params[k].grad is None or f"{ref_name}/grad/{k}/val" not in out:
+            continue
+        s = mg.sample(params[k].grad)
+        mg.pack(f"{name}/grad/{k}", s, out)
+        ref32 = out[f"{ref_name}/grad/{k}/val"].astype(np.float64)
+        exact = s["val"].astype(np.float64)                      # float32 storage of the float64 values: 6e-8 relative
+        dev[k] = float(np.abs(ref32 - exact).max() / max(np.abs(exact).max(), 1e-30))
+    meta[name] = {"kind": "train_fp64", "channels": channels, "shape": list(shape), "batch": batch, "seed": seed,
+                  "reference_fp32_deviation": dev}
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_model, ref_crit = mg.import_reference()
     out, meta = {}, {}
     mg.train_case(ref_model, ref_crit, "train64", [16, 32, 64, 128, 256], (64, 64, 64), 2, 31, out, meta)
+    oracle_fp64_case("train64_fp64", "train64", [16, 32, 64, 128, 256], (64, 64, 64), 2, 31, out, meta)
     mg.eval_case(ref_model, "eval128_full", [32, 64, 128, 256, 512], (128, 128, 128), 1, 19, out, meta)
     for v in meta.values():
         v.pop("state_keys", None)
