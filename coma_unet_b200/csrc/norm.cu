@@ -438,6 +438,213 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_small_kernel(coma_affine_a
     }
 }
 
+
+// ---- bulk-copy streaming variants of the two backward sweeps (bf16, contiguous tensors) ------------------------------------
+// The register-staged sweeps above top out near half of the HBM peak: bytes in flight cost registers (126 regs, two blocks per
+// SM in the reduce sweep).  Here a ring of shared-memory stages is filled by cp.async.bulk (one elected thread issues 16 KB
+// copies that complete on an mbarrier), so ~100 KB per SM are in flight whatever the compute part needs, and the 256 threads
+// only read shared memory.  A tile is kTileBytes of each operand = 1024 16-byte vectors; thread t owns vectors t, t+256, ...:
+// kThreads is a multiple of the C/8 vectors of a voxel, so a thread always sees the same 8 channels (coefficients in registers).
+constexpr int kTileBytes = 16384;
+constexpr int kTileVecs = kTileBytes / 16;
+constexpr int kBulkStages = 3;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bulk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();   // watchdog: a lost copy must not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void unpack8_u4(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+struct BulkRing {
+  const char* src[3];      // x, dy, residual (contiguous [V, C] bf16 of sample b, offset to the block's first voxel)
+  int nsrc;
+  int64_t bytes;           // bytes of each operand this block sweeps
+};
+
+// Issue the copies of tile `t` into stage `t % kBulkStages` (nsrc operand slots per stage).  Called by one thread.
+__device__ __forceinline__ void bulk_issue(const BulkRing& ring, char* stage_base, uint64_t* full, int t) {
+  const int s = t % kBulkStages;
+  const int64_t off = (int64_t)t * kTileBytes;
+  const uint32_t n = (uint32_t)min((int64_t)kTileBytes, ring.bytes - off);
+  bulk_mbar_expect_tx(&full[s], n * ring.nsrc);
+  for (int i = 0; i < ring.nsrc; ++i)
+    bulk_load(stage_base + ((size_t)s * ring.nsrc + i) * kTileBytes, ring.src[i] + off, n, &full[s]);
+}
+
+// MODE 0: reduce sweep (partial sums of dz, dz*xhat, dslope terms).  MODE 1: apply sweep (dx = P*dz + Q + R*x, optional dr = dz).
+template <int MODE, bool SIMPLE, bool HASR>
+__global__ void __launch_bounds__(kThreads, 2) bwd_bulk_kernel(coma_affine_act_bwd_args a, int chunks) {
+  extern __shared__ __align__(128) char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // [kBulkStages]
+  constexpr int NS = HASR ? 3 : 2;
+  char* stages = smem + 128;                                           // [kBulkStages][NS][kTileBytes]
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int C = a.C, CV = C >> 3;
+  const int cvec = tid % CV;
+  // chunk boundaries in voxels, rounded so that every chunk starts on a tile boundary of whole voxels
+  const int tile_vox = kTileVecs / CV;
+  const int64_t tiles_total = (a.V + tile_vox - 1) / tile_vox;
+  const int64_t tiles_per = (tiles_total + chunks - 1) / chunks;
+  const int64_t v0 = min((int64_t)chunk * tiles_per * tile_vox, a.V), v1 = min(v0 + tiles_per * tile_vox, a.V);
+  const int ntiles = (int)((v1 - v0 + tile_vox - 1) / tile_vox);
+  BulkRing ring;
+  const int64_t row = (int64_t)C * 2;
+  ring.src[0] = static_cast<const char*>(a.x) + ((int64_t)b * a.V + v0) * row;
+  ring.src[1] = static_cast<const char*>(a.dy) + ((int64_t)b * a.V + v0) * row;
+  ring.src[2] = HASR ? static_cast<const char*>(a.r) + ((int64_t)b * a.V + v0) * row : nullptr;
+  ring.nsrc = NS;
+  ring.bytes = (v1 - v0) * row;
+  if (tid == 0) {
+    for (int s = 0; s < kBulkStages; ++s) bulk_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < min(kBulkStages, ntiles); ++t) bulk_issue(ring, stages, full, t);
+
+  float A8[8], S8[8], M8[8], R8[8], P8[8], Q8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int64_t i = (int64_t)b * C + cvec * 8 + e;
+    A8[e] = a.A[i]; S8[e] = a.S[i];
+    if (MODE == 0) { M8[e] = a.mean[i]; R8[e] = a.rstd[i]; }
+    else { P8[e] = a.coef[i * 3]; Q8[e] = a.coef[i * 3 + 1]; R8[e] = a.coef[i * 3 + 2]; }
+  }
+  const float slope = a.slope ? __ldg(a.slope) : 0.f;
+  const float gneg = a.act == COMA_ACT_NONE ? 1.f : (a.act == COMA_ACT_RELU ? 0.f : slope);
+  const float sflag = a.act == COMA_ACT_LEAKY ? 1.f : 0.f;
+  float acc[8][3];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e][0] = acc[e][1] = acc[e][2] = 0.f;
+  __nv_bfloat16* dxb = MODE == 1 ? static_cast<__nv_bfloat16*>(a.dx) + ((int64_t)b * a.V + v0) * C : nullptr;
+  __nv_bfloat16* drb = (MODE == 1 && a.dr) ? static_cast<__nv_bfloat16*>(a.dr) + ((int64_t)b * a.V + v0) * C : nullptr;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kBulkStages;
+    bulk_mbar_wait(&full[s], (uint32_t)(t / kBulkStages) & 1u);
+    const int64_t off = (int64_t)t * kTileBytes;
+    const int nvec = (int)(min((int64_t)kTileBytes, ring.bytes - off) >> 4);
+    const uint4* sx = reinterpret_cast<const uint4*>(stages + ((size_t)s * NS + 0) * kTileBytes);
+    const uint4* sd = reinterpret_cast<const uint4*>(stages + ((size_t)s * NS + 1) * kTileBytes);
+    const uint4* sr = reinterpret_cast<const uint4*>(stages + ((size_t)s * NS + (HASR ? 2 : 0)) * kTileBytes);
+#pragma unroll
+    for (int j = 0; j < kTileVecs / kThreads; ++j) {
+      const int vi = tid + j * kThreads;
+      if (vi < nvec) {
+        float xv[8], dyv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unpack8_u4(sx[vi], xv);
+        unpack8_u4(sd[vi], dyv);
+        if (HASR) unpack8_u4(sr[vi], rv);
+        if (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
+            const float dz = dyv[e] * (SIMPLE ? (u > 0.f ? 1.f : gneg) : act_grad(a.act, u, slope));
+            acc[e][0] += dz;
+            acc[e][1] += dz * (xv[e] - M8[e]) * R8[e];
+            acc[e][2] += SIMPLE ? sflag * dyv[e] * fminf(u, 0.f) : dyv[e] * act_slope_grad(a.act, u, slope);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float u = fmaf(A8[e], xv[e], S8[e]) + rv[e];
+            const float dz = dyv[e] * (SIMPLE ? (u > 0.f ? 1.f : gneg) : act_grad(a.act, u, slope));
+            xv[e] = fmaf(P8[e], dz, fmaf(R8[e], xv[e], Q8[e]));
+            rv[e] = dz;
+          }
+          const int64_t eoff = (off >> 1) + (int64_t)vi * 8;          // element offset inside the block's range
+          store8(dxb + eoff, xv);
+          if (drb) store8(drb + eoff, rv);
+        }
+      }
+    }
+    __syncthreads();                                                   // every thread is done with stage s
+    if (tid == 0 && t + kBulkStages < ntiles) bulk_issue(ring, stages, full, t + kBulkStages);
+  }
+  if (MODE == 0) {
+    // block reduction over the threads that share a channel vector (the stage buffers are free now)
+    float* red = reinterpret_cast<float*>(stages);                     // [kThreads][24]
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) red[tid * 24 + e * 3 + q] = acc[e][q];
+    __syncthreads();
+    const int lanes = kThreads / CV;
+    for (int i = tid; i < C * 3; i += kThreads) {
+      const int c = i / 3, q = i % 3;
+      float sum = 0.f;
+      for (int l = 0; l < lanes; ++l) sum += red[(l * CV + (c >> 3)) * 24 + (c & 7) * 3 + q];
+      a.partial[(((int64_t)b * chunks + chunk) * C + c) * 3 + q] = sum;
+    }
+  }
+}
+
+constexpr size_t bulk_smem(bool hasr) { return 128 + (size_t)kBulkStages * (hasr ? 3 : 2) * kTileBytes; }   // 96 KB: two blocks per SM
+
+static bool bulk_ok(const coma_affine_act_bwd_args* a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_NORM_BULK"); return e && atoi(e) != 0; }();
+  if (off || a->dtype != COMA_BF16) return false;
+  const int C = a->C;
+  if (C < 8 || (C & (C - 1)) != 0 || C > 512) return false;          // C/8 must divide kThreads
+  if (a->x_cs != C || a->x_co != 0 || a->dy_cs != C || a->dy_co != 0 || a->dx_cs != C || a->dx_co != 0) return false;
+  if (a->r && a->r_cs != C) return false;
+  if (a->dr && a->dr_cs != C) return false;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(a->x) || !al(a->dy) || !al(a->dx) || (a->r && !al(a->r)) || (a->dr && !al(a->dr))) return false;
+  return a->V * C >= 4 * kTileVecs * 8;                                // small tensors: the plain sweeps are latency-bound anyway
+}
+
+template <int MODE>
+static int launch_bulk(const coma_affine_act_bwd_args* a, int chunks, cudaStream_t stream) {
+  const bool simple = a->act == COMA_ACT_NONE || a->act == COMA_ACT_RELU || a->act == COMA_ACT_LEAKY;
+  dim3 grid((unsigned)chunks, (unsigned)a->B);
+#define COMA_BULK_LAUNCH(S, R)                                                                                          \
+  do {                                                                                                                   \
+    static bool attr = false;                                                                                            \
+    if (!attr) {                                                                                                         \
+      cudaFuncSetAttribute(bwd_bulk_kernel<MODE, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(R));  \
+      attr = true;                                                                                                       \
+    }                                                                                                                    \
+    bwd_bulk_kernel<MODE, S, R><<<grid, kThreads, bulk_smem(R), stream>>>(*a, chunks);                                    \
+  } while (0)
+  if (simple && !a->r) COMA_BULK_LAUNCH(true, false);
+  else if (simple) COMA_BULK_LAUNCH(true, true);
+  else if (!a->r) COMA_BULK_LAUNCH(false, false);
+  else COMA_BULK_LAUNCH(false, true);
+#undef COMA_BULK_LAUNCH
+  COMA_CHECK_LAUNCH(MODE == 0 ? "norm_bwd_reduce_bulk" : "norm_bwd_apply_bulk");
+  return COMA_OK;
+}
+
 }  // namespace coma
 
 using namespace coma;
@@ -520,6 +727,15 @@ extern "C" int coma_norm_film_act_bwd(const coma_affine_act_bwd_args* a, coma_st
   COMA_CHECK_ARG(a && a->x && a->dy && a->dx && a->A && a->S && a->mean && a->rstd && a->partial && a->dg && a->dh && a->coef,
                  "coma_norm_film_act_bwd: bad arguments");
   const int chunks = stats_chunks(a->V);
+  if (bulk_ok(a)) {
+    int rc = launch_bulk<0>(a, chunks, stream);
+    if (rc) return rc;
+    bwd_finalize_kernel<<<(unsigned)a->C, kThreads, 0, stream>>>(*a, chunks);
+    COMA_CHECK_LAUNCH("norm_bwd_finalize");
+    // apply sweep: enough blocks for ~4 waves of two blocks per SM
+    const int ach = std::max(1, (4 * 2 * num_sms() + a->B - 1) / a->B);
+    return launch_bulk<1>(a, ach, stream);
+  }
   BwdCtx ctx{a->dy, a->A, a->S, a->mean, a->rstd, a->slope, a->dy_cs, a->dy_co, a->act, a->r, a->r_cs};
   int rc;
   if (a->dtype == COMA_BF16)

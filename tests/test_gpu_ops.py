@@ -200,11 +200,31 @@ def norm_reference(x, g, h, slope, mode, act, rm, rv, residual, eps=1e-5):
     return u
 
 
+# shapes big enough for the bulk-copy streaming sweeps of the backward (bf16, contiguous, V*C >= 32768): whole tiles, a ragged
+# last tile, more chunks than tiles, one 16-voxel tile per 512-channel row block
+NORM_BULK_CASES = [
+    (L.NORM_BATCH, L.ACT_RELU, 32, True, False, (2, 16, 16, 16)),
+    (L.NORM_INSTANCE, L.ACT_LEAKY, 16, True, False, (2, 17, 18, 20)),
+    (L.NORM_BATCH, L.ACT_RELU, 16, False, True, (2, 12, 16, 24)),
+    (L.NORM_INSTANCE, L.ACT_LEAKY_RELU, 8, False, False, (1, 20, 24, 16)),
+    (L.NORM_BATCH, L.ACT_RELU, 256, True, False, (2, 8, 8, 8)),
+    (L.NORM_BATCH, L.ACT_RELU, 512, False, False, (3, 4, 4, 4)),
+    (L.NORM_BATCH, L.ACT_SIGMOID, 64, False, True, (1, 9, 10, 12)),
+    (L.NORM_INSTANCE, L.ACT_NONE, 128, False, False, (2, 16, 16, 16)),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", NORM_BULK_CASES)
+def test_norm_film_act_fwd_bwd_streaming_sizes(case, dtype):
+    test_norm_film_act_fwd_bwd(case[:5], dtype, shape=case[5])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("case", NORM_CASES)
-def test_norm_film_act_fwd_bwd(case, dtype):
+def test_norm_film_act_fwd_bwd(case, dtype, shape=(2, 6, 5, 8)):
     mode, act, Cn, film, use_res = case
-    B, D, H, W = 2, 6, 5, 8
+    B, D, H, W = shape
     x = rnd(B, Cn, D, H, W, seed=20) * 1.5 + 0.3
     res = rnd(B, Cn, D, H, W, seed=26) if use_res else None
     if dtype == torch.bfloat16:
