@@ -431,14 +431,18 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
     mri, tau, roi, covars, dicts = make_batch(nb, 1234 + rank, shape, device=device, mixed=(name == "c5"))
     h_mri, h_tau, h_roi, h_cov, _ = make_batch(nb, 1234 + rank, shape, pin=True, mixed=(name == "c5"))
     engine = None
+    use_graph = not args.no_graph
     if train:
+        from coma_unet_b200.graph import GraphedTrainStep
         from coma_unet_b200.parallel import DataParallelEngine
         model.train(True)
         crit = build_criterion()
         engine = DataParallelEngine(model, world_size=world)
-        opt = torch.optim.AdamW(model.parameters(), 1e-3, fused=True)     # the same optimizer train_dp builds
+        # the optimizer train_dp builds: fused AdamW (capturable + tensor learning rate when the step is replayed from a CUDA graph)
+        opt = GraphedTrainStep.make_optimizer(model, 1e-3) if use_graph else torch.optim.AdamW(model.parameters(), 1e-3, fused=True)
+        graphed = GraphedTrainStep(model, crit, opt, engine) if use_graph else None
 
-        def step(m=mri, t=tau, r=roi, c=covars):
+        def eager_step(m=mri, t=tau, r=roi, c=covars):
             opt.zero_grad(set_to_none=True)
             pred, proj, final = model(m, c, roi_pred_dicts=dicts, sample_roi_mask=r)
             feats, labels = engine.gather_rnc(proj[-1], c[:, -1].float().to(device, non_blocking=True))
@@ -448,15 +452,23 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
             engine.finish()
             opt.step()
             return loss
-    else:
-        model.eval()
-        model.set_training(False)
 
         def step(m=mri, t=tau, r=roi, c=covars):
+            return graphed(m, t, r, c, dicts) if use_graph else eager_step(m, t, r, c)
+    else:
+        from coma_unet_b200.graph import GraphedInference
+        model.eval()
+        model.set_training(False)
+        graphed = GraphedInference(model) if use_graph and batch else None
+
+        def eager_step(m=mri, t=tau, r=roi, c=covars):
             if batch == 0:
                 return None
             with torch.no_grad():
                 return model(m, c, roi_pred_dicts=dicts, sample_roi_mask=r)
+
+        def step(m=mri, t=tau, r=roi, c=covars):
+            return graphed(m, c, dicts, r) if graphed is not None else eager_step(m, t, r, c)
 
     def timed_steps(n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -466,7 +478,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
         e1.record()
         return e0, e1
 
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, 5 if use_graph else 3)       # graph replay: 2 eager steps + the capture come first
     with ClockSampler(local) as clocks:           # sampling starts with the warm-up (same load) and is windowed to the timed region
         for _ in range(warm - 2):
             step()
@@ -495,7 +507,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
         if engine.enabled:
             engine.timing, engine.timing_events = True, []
             for _ in range(10):
-                step()
+                eager_step()
             torch.cuda.synchronize()
             engine.timing = False
             exposed = [a.elapsed_time(b) for a, b in engine.timing_events]
@@ -550,7 +562,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
     # ---- roofline of the dominant kernel family (instrumented extra pass, not part of the timing above) ----
     roofline = hbm_roof = None
     if batch:
-        fam, layers, hbm, timeline = kernel_profile(step)
+        fam, layers, hbm, timeline = kernel_profile(eager_step)
         roofline, hbm_roof = roofline_records(fam, layers, hbm, peaks, clk, "r02_ncu_conv_kernels_summary.json")
         if rank == 0 and args.profile_out:
             with open(args.profile_out.replace(".json", f"_{name}.json") if args.mode == "both" and not args.config else args.profile_out, "w") as f:
@@ -569,6 +581,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
                    "channels": CHANNELS, "per_gpu_batch": batch if name != "c4" else (global_batch + world - 1) // world,
                    "global_batch": global_batch, "parallelism": f"dp{world}", "active_gpus": n_active,
                    "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
+                   "launch": "CUDA graph replay (coma_unet_b200.graph), one graph per step" if use_graph else "eager (one ABI call per kernel)",
                    "gflop_per_volume_algorithmic": gflop, "model_tflops": value * gflop / 1e3,
                    "model_frac_of_peak": value * gflop / 1e3 / (peaks["tflops"] * max(n_active, 1)),
                    "peak_hbm_allocated_GiB": peak_mem},
@@ -578,7 +591,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
     }
     if comm is not None:
         rec["comm"] = comm
-    del model, mri, tau, roi, h_mri, h_tau, h_roi, sink
+    del model, mri, tau, roi, h_mri, h_tau, h_roi, sink, graphed, step, eager_step
     if train:
         del opt, engine
     torch.cuda.empty_cache()
@@ -625,6 +638,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (c4: the GLOBAL batch split over the ranks)")
     ap.add_argument("--min-seconds", type=float, default=3.0, help="minimum length of the timed window")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -10,10 +10,11 @@ from .criterions import GenerativeContrastiveLoss, RnCLoss, RoiMSE
 from .data import DevicePrefetcher, HostSink, SyntheticVolumeDataset, prepare_geometry, prepare_volumes
 from .model import (AttentionLayer, ContrastiveAttentionUNET_DP, ObservableAttentionBlock, ObservableAttentionUnet,
                     ProjectionHead, StackedFusionConvLayers, UpBlock)
+from .graph import GraphedInference, GraphedTrainStep
 from .parallel import DataParallelEngine
 from .train import train_dp
 
 __all__ = ["ContrastiveAttentionUNET_DP", "ObservableAttentionUnet", "AttentionLayer", "ObservableAttentionBlock",
            "UpBlock", "ProjectionHead", "StackedFusionConvLayers", "RoiMSE", "RnCLoss", "GenerativeContrastiveLoss",
            "SyntheticVolumeDataset", "DevicePrefetcher", "HostSink", "DataParallelEngine", "train_dp", "metrics", "_lib",
-           "prepare_geometry", "prepare_volumes"]
+           "prepare_geometry", "prepare_volumes", "GraphedTrainStep", "GraphedInference"]

@@ -299,7 +299,7 @@ class AttentionBlock(nn.Module):
     def _fold(self):
         mods = (self.W_g[0].conv, self.W_g[1], self.W_x[0].conv, self.W_x[1], self.psi[0].conv, self.psi[1])
         key = tuple(t._version for m in mods for t in list(m.parameters()) + list(m.buffers())) + \
-            (self.W_g[0].conv.weight.device,)
+            (self.W_g[0].conv.weight.device, ops.weight_epoch())
         if key == self._fold_key:
             return self._folded
         with torch.no_grad():

@@ -47,7 +47,7 @@ class FilmBatch:
 
     def _stacked(self, device):
         params = [p for m in self.mods for p in m.film.parameters()]
-        key = (str(device),) + tuple((p._version, p.data_ptr()) for p in params)
+        key = (str(device), ops.weight_epoch()) + tuple((p._version, p.data_ptr()) for p in params)
         if key != self._key:
             L = len(self.mods)
             nmax = max(m.num_covars for m in self.mods)

@@ -160,6 +160,10 @@ class ObservableAttentionUnet(nn.Module):
                 break
             layer = sub[-1]
 
+    def train(self, mode: bool = True):
+        ops.bump_weight_epoch()          # derived-weight caches never survive a train()/eval() switch (see ops.pack_weight)
+        return super().train(mode)
+
     def set_compute_dtype(self, dtype):
         assert dtype in (torch.float32, torch.bfloat16)
         self.compute_dtype = dtype
@@ -196,6 +200,8 @@ class ObservableAttentionUnet(nn.Module):
                 cond_conv.FilmBatch.clear()
 
     def forward(self, x, covariate=None):
+        if self.training:
+            ops.bump_weight_epoch()      # the optimizer may have stepped since the last forward
         if covariate is not None:
             covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
@@ -284,6 +290,7 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         self._roi_ids = None
 
     def set_training(self, mode):
+        ops.bump_weight_epoch()
         self.training = mode
 
     def get_depth(self):
@@ -295,7 +302,8 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         return [self.pos_dynamic_prompt, self.neg_dynamic_prompt]
 
     # -- ROI lookup table: host dicts -> one small pinned upload, no per-ROI device work ---------------
-    def _roi_lut(self, roi_pred_dicts, device):
+    def roi_lut_host(self, roi_pred_dicts):
+        """[B, 36, 2] float32 (loc, std) table of the per-sample ROI prediction dicts, on the host (numpy)."""
         B = len(roi_pred_dicts)
         lut = np.empty((B, len(self.roi_indices), 2), dtype=np.float32)
         for b, d in enumerate(roi_pred_dicts):
@@ -303,11 +311,16 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
                 entry = d[self.roi_ind_names_dict[idx]]
                 lut[b, i, 0] = np.nan_to_num(entry["loc"])
                 lut[b, i, 1] = np.nan_to_num(entry["std"])
-        t = torch.from_numpy(lut)
-        if device.type == "cuda":
-            t = t.pin_memory().to(device, non_blocking=True)
+        return lut
+
+    def _roi_lut(self, roi_pred_dicts, device):
         if self._roi_ids is None or self._roi_ids.device != device:
             self._roi_ids = torch.tensor(self.roi_indices, dtype=torch.int32, device=device)
+        if torch.is_tensor(roi_pred_dicts):      # a table already on the device (coma_unet_b200.graph keeps it in a static buffer)
+            return roi_pred_dicts
+        t = torch.from_numpy(self.roi_lut_host(roi_pred_dicts))
+        if device.type == "cuda":
+            t = t.pin_memory().to(device, non_blocking=True)
         return t
 
     def forward_modulator_with_uq(self, x, out, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
@@ -320,7 +333,9 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         cov0 = covariate.reshape(B, -1)[:, 0]
         is_pos = (cov0 == 1).to(device=dev, dtype=torch.float32)
         used = (True, True)
-        if torch.is_grad_enabled() and (self.pos_dynamic_prompt.requires_grad or self.neg_dynamic_prompt.requires_grad):
+        if getattr(self, "_prompt_use_override", None) is not None:
+            used = tuple(self._prompt_use_override)      # decided by the caller (graph replay: the flags are part of the graph's key)
+        elif torch.is_grad_enabled() and (self.pos_dynamic_prompt.requires_grad or self.neg_dynamic_prompt.requires_grad):
             # which prompts get a gradient at all (None otherwise, like the reference's .item() branch, :638-639)
             flags = getattr(self, "_host_flags", None)
             if flags is None:
@@ -342,11 +357,18 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         return self.final_pred_head(pair, final_relu=True)                             # conv1x1 + IN + PReLU, then ReLU
 
     def forward(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
+        if getattr(self, "_coma_stale_caches", False) and getattr(self, "_prompt_use_override", None) is None:
+            # eager call after CUDA-graph replays of the training step (coma_unet_b200.graph): the replays updated the parameters
+            # without bumping the version counters the packed-weight / folded-BatchNorm caches are keyed on
+            ops.invalidate_weight_caches(self)
+            self._coma_stale_caches = False
+        if self.training or any(m.training for m in (self.model[0], self.model[2])):
+            ops.bump_weight_epoch()      # the optimizer may have stepped since the last forward (fused optimizers bump no version counter)
         self._host_flags = None
         if covariate is not None:   # one H2D copy / cast per forward instead of one per conditioned layer
             if not covariate.is_cuda:
                 self._host_flags = covariate.reshape(covariate.shape[0], -1)[:, 0] == 1     # no device sync needed
-            elif torch.is_grad_enabled():
+            elif torch.is_grad_enabled() and getattr(self, "_prompt_use_override", None) is None:
                 # covariates already on the device: read the positive/negative flags back into pinned memory now and look at
                 # them only in backward (ops.RoiPaintFn), so that the forward never waits for the GPU
                 host = torch.empty(covariate.shape[0], dtype=torch.bool, pin_memory=True)

@@ -75,14 +75,33 @@ def _round_up(n: int, m: int) -> int:
 # ------------------------------------------------------------------------------------------------
 # weight packing (cached)
 # ------------------------------------------------------------------------------------------------
+# Derived-weight caches (packed conv weights, folded BatchNorm, stacked FiLM MLPs) are keyed by the parameters' version counters
+# AND by this epoch.  The version counter alone is not enough: torch's FUSED optimizers (``AdamW(fused=True)``, which train_dp
+# uses) update parameters in place without bumping it -- measured: with the version-only key the convolutions kept using the
+# weights packed in the first step while every directly-read parameter trained.  The model classes bump the epoch at the start
+# of every training-mode forward and on every train()/eval() switch, so a pack is reused only within one training step
+# (forward + backward) or across consecutive eval-mode forwards.
+_EPOCH = 0
+
+
+def bump_weight_epoch() -> None:
+    global _EPOCH
+    _EPOCH += 1
+
+
+def weight_epoch() -> int:
+    return _EPOCH
+
+
 def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp: int, dtype: torch.dtype) -> torch.Tensor:
     """Conv3d ``[Cout,Cin,k,k,k]`` / ConvTranspose3d ``[Cin,Cout,k,k,k]`` -> ``[k^3, cout_comp, cin_buf]`` (zero padded).
 
-    Cached on the parameter object itself (so the cache dies with it) and keyed by its version counter and storage."""
+    Cached on the parameter object itself (so the cache dies with it) and keyed by its version counter, its storage and the
+    weight epoch (see above)."""
     cache = weight.__dict__.setdefault("_coma_packed", {})
     key = (transposed, cin_buf, cout_comp, dtype)
     hit = cache.get(key)
-    if hit is not None and hit[0] == (weight._version, weight.data_ptr(), weight.device):
+    if hit is not None and hit[0] == (weight._version, weight.data_ptr(), weight.device, _EPOCH):
         return hit[1]
     w = weight.detach()
     k = w.shape[2]
@@ -96,16 +115,18 @@ def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp:
         q[:, :p.shape[1], :p.shape[2]] = p
         p = q
     p = p.to(dtype).contiguous()
-    cache[key] = ((weight._version, weight.data_ptr(), weight.device), p)
+    cache[key] = ((weight._version, weight.data_ptr(), weight.device, _EPOCH), p)
     return p
 
 
 def invalidate_weight_caches(module: torch.nn.Module) -> None:
     """Drop every cached packed weight / folded BatchNorm of ``module``.
 
-    The caches are keyed by the parameters' version counters, which in-place updates through ``.data`` (EMA swaps, manual
-    clipping on ``p.data``) do not bump: call this after such an update.  ``load_state_dict``, optimizers and ``copy_`` under
-    ``no_grad`` do bump the counter and need nothing."""
+    The caches are keyed by the parameters' version counters and the weight epoch (``bump_weight_epoch``).  In-place updates
+    through ``.data`` (EMA swaps, manual clipping on ``p.data``) and fused optimizers bump neither: after such an update of a
+    model that stays in eval mode, call this (training-mode forwards and train()/eval() switches refresh the caches by
+    themselves)."""
+    bump_weight_epoch()
     for p in module.parameters():
         p.__dict__.pop("_coma_packed", None)
     for m in module.modules():

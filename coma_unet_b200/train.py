@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
+from .graph import GraphedTrainStep
 from .parallel import DataParallelEngine
 
 
@@ -60,6 +61,7 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
     roi_pred_fn = kwargs["roi_pred_fn"]
     val_iter = kwargs.get("val_iter", 5)
     checkpoint_iter = kwargs.get("checkpoint_iter", 5)
+    cuda_graph = bool(kwargs.get("cuda_graph", False))       # replay the step from a CUDA graph (coma_unet_b200.graph)
     criterion.gen_loss.batch_reduction = None
     start_epoch = 0
     if from_checkpoint:
@@ -67,10 +69,14 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
         start_epoch = kwargs["start_epoch"]
         scheduler = kwargs.get("scheduler") or ReduceLROnPlateau(optimizer, "min", patience=5, factor=0.2)
     else:
-        optimizer = torch.optim.AdamW(model.parameters(), lr, fused=next(model.parameters()).is_cuda)   # one multi-tensor kernel per step
+        if cuda_graph:      # capturable fused AdamW with a tensor learning rate (ReduceLROnPlateau fills it in place)
+            optimizer = GraphedTrainStep.make_optimizer(model, lr)
+        else:
+            optimizer = torch.optim.AdamW(model.parameters(), lr, fused=next(model.parameters()).is_cuda)   # one multi-tensor kernel per step
         scheduler = ReduceLROnPlateau(optimizer, "min", patience=5)
     engine = DataParallelEngine(model) if dist.is_available() and dist.is_initialized() else DataParallelEngine(model, world_size=1)
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    graphed = GraphedTrainStep(model, criterion, optimizer, engine) if cuda_graph else None
     history = {"epoch_avg_loss": [], "epoch_avg_gen_loss": [], "val_mae": []}
     ckpt_dir = os.path.join(save_path, "checkpoints") if save_path else ""
     if ckpt_dir and rank == 0:
@@ -85,6 +91,12 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
         for batch in train_loader:
             mri, tau, roi, _, covars, paths = _unpack(batch)
             mri, tau, roi = mri.to(device, non_blocking=True), tau.to(device, non_blocking=True), roi.to(device, non_blocking=True)
+            if graphed is not None and graphed.matches(mri):
+                loss = graphed(mri, tau, roi, covars, roi_pred_fn(paths))
+                loss_sum += loss
+                gen_sum += graphed.gen_loss.sum()
+                num_samples += mri.shape[0]
+                continue
             optimizer.zero_grad(set_to_none=True)
             pred, projected, final_repr = model(mri, covars, roi_pred_dicts=roi_pred_fn(paths), sample_roi_mask=roi)[:3]
             feats, labels = engine.gather_rnc(projected[-1], covars[:, -1].float().to(device))       # :842-845

@@ -318,6 +318,113 @@ def test_train_loop_checkpoints_and_resumes(tmp_path):
     assert len(hist2["epoch_avg_loss"]) == 1 and hist2["epoch_avg_loss"][0] < hist["epoch_avg_loss"][1] * 1.2
 
 
+def test_graphed_train_step_matches_eager_steps():
+    """coma_unet_b200.graph: four optimizer steps replayed from CUDA graphs (two eager warm-up steps, then one graph per
+    prompt-usage key) leave the model where four eager steps leave it -- including a batch that selects only the negative prompt
+    (its own graph: pos_dynamic_prompt gets no gradient and AdamW must not touch it, attn_unet_data_parallel.py:638-639) -- and an
+    eager forward afterwards sees the updated weights."""
+    from coma_unet_b200.graph import GraphedInference, GraphedTrainStep
+    from coma_unet_b200.parallel import DataParallelEngine
+    case = {"channels": [8, 16, 32, 64, 128], "shape": [32, 32, 32], "batch": 2, "seed": 9}
+    batches = []
+    for i, first in enumerate((None, None, None, 0.0, None, 0.0)):
+        mri, tau, roi, covars, dicts = common.synthetic_batch(2, case["shape"], 90 + i)
+        if first is not None:
+            covars[:, :, 0] = first
+        else:
+            covars[0, 0, 0], covars[1, 0, 0] = 1.0, 0.0
+        batches.append((mri.to(DEV), tau.to(DEV), roi.to(DEV), covars, dicts))
+
+    def run(graph):
+        m = build(case, torch.float32)
+        m.train(True)
+        crit = criterion(cu)
+        eng = DataParallelEngine(m, world_size=1)
+        opt = GraphedTrainStep.make_optimizer(m, 1e-3)
+        runner = GraphedTrainStep(m, crit, opt, eng) if graph else None
+        losses, pos_before = [], None
+        for k, (mri, tau, roi, covars, dicts) in enumerate(batches):
+            if k == 3:
+                pos_before = m.pos_dynamic_prompt.detach().clone()
+            if graph:
+                losses.append(runner(mri, tau, roi, covars, dicts).clone())
+            else:
+                opt.zero_grad(set_to_none=True)
+                pred, proj, final = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+                z = torch.zeros(final.size(), device=DEV)
+                loss, _, _, _ = crit(pred, tau, roi, (final, z, z), (proj[-1], covars[:, -1].float().to(DEV)))
+                loss.backward()
+                opt.step()
+                losses.append(loss.detach().clone())
+            if k == 3:
+                assert torch.equal(m.pos_dynamic_prompt.detach(), pos_before), "a prompt nobody selected was updated"
+        if graph:
+            assert runner.replays == len(batches) - 2 and set(runner.graphs) == {(True, True), (False, True)}
+        m.eval()
+        m.set_training(False)
+        mri, tau, roi, covars, dicts = batches[0]
+        with torch.no_grad():
+            pred = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi).clone()
+        if graph:       # the inference graph replays to the same prediction
+            inf = GraphedInference(m)
+            for _ in range(4):
+                got = inf(mri, covars, dicts, roi)
+            assert torch.allclose(got, pred, rtol=1e-5, atol=1e-6)
+        return torch.stack(losses).cpu(), {k: v.detach().clone() for k, v in m.state_dict().items()}, pred
+
+    le, se, pe = run(False)
+    lg, sg, pg = run(True)
+    # Adam normalises every gradient by its own magnitude, so run-to-run rounding noise in a near-zero gradient (fp32 atomics in the
+    # weight-gradient kernels) becomes a +-lr difference in that weight: the losses agree to 1e-3, every weight to within the
+    # 2 * lr * steps such sign flips can move it, and the weights on average far better than that.
+    assert torch.allclose(lg, le, rtol=1e-3), (lg, le)
+    lr, steps = 1e-3, len(batches)
+    diffs = []
+    for k in se:
+        if se[k].dtype.is_floating_point:
+            d = (sg[k] - se[k]).abs()
+            scale = float(se[k].abs().max()) + 1e-12
+            if "running" in k:      # BatchNorm statistics of activations: they follow the weights' +-lr noise through the network
+                assert float(d.max()) <= 5e-2 * scale + 2e-2, (k, float(d.max()))
+                continue
+            assert float(d.max()) <= 2 * lr * steps + 1e-3 * scale, (k, float(d.max()))
+            diffs.append(float(d.mean()))
+        else:
+            assert torch.equal(sg[k], se[k]), k
+    assert sum(diffs) / len(diffs) < 0.1 * lr, sum(diffs) / len(diffs)
+    assert check.scaled_err(pg.cpu().numpy(), pe.cpu().numpy()) < 2e-2
+
+
+def test_fused_optimizer_updates_reach_the_packed_weights():
+    """torch's fused AdamW updates parameters in place WITHOUT bumping their version counters; a packed-weight cache keyed on the
+    version alone keeps convolving with the weights of the first step (found in round 2: the loss after one step read 31.6 instead
+    of 23.6).  Two steps with the fused optimizer must give the losses of the plain single-tensor implementation."""
+    case = {"channels": [8, 16, 32, 64, 128], "shape": [32, 32, 32], "batch": 2, "seed": 9}
+    mri, tau, roi, covars, dicts = common.synthetic_batch(2, case["shape"], 92)
+    mri, tau, roi = mri.to(DEV), tau.to(DEV), roi.to(DEV)
+    losses = {}
+    for kind, kw in (("single", dict(foreach=False, fused=False)), ("fused", dict(fused=True))):
+        for dtype in (torch.float32, torch.bfloat16):
+            m = build(case, dtype)
+            m.train(True)
+            crit = criterion(cu)
+            opt = torch.optim.AdamW(m.parameters(), lr=1e-3, **kw)
+            out = []
+            for _step in range(3):
+                opt.zero_grad(set_to_none=True)
+                pred, proj, final = m(mri, covars, roi_pred_dicts=dicts, sample_roi_mask=roi)
+                z = torch.zeros(final.size(), device=DEV)
+                loss = crit(pred, tau, roi, (final, z, z), (proj[-1], covars[:, -1].float().to(DEV)))[0]
+                loss.backward()
+                opt.step()
+                out.append(float(loss.detach()))
+            losses[kind, dtype] = out
+    for dtype, tol in ((torch.float32, 2e-3), (torch.bfloat16, 2e-2)):
+        a, b = losses["single", dtype], losses["fused", dtype]
+        assert a[1] < 0.9 * a[0], a                       # the step does reduce the loss on this batch
+        assert all(abs(x - y) < tol * abs(x) for x, y in zip(a, b)), (dtype, a, b)
+
+
 def test_prefetcher_and_sink_stream_batches_in_order():
     """DevicePrefetcher / HostSink (the pinned DataLoader + non_blocking idiom): every batch arrives intact and in order
     on the compute stream, and every result lands in host memory."""
