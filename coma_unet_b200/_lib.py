@@ -139,6 +139,7 @@ EXPORTS = {
     "coma_roi_mse_bwd": (C.c_int, [C.POINTER(RoiMseArgs), _vp]),
     "coma_eval_metrics": (C.c_int, [C.POINTER(EvalMetricsArgs), _vp]),
     "coma_prepare_volumes": (C.c_int, [C.POINTER(PrepareArgs), _vp]),
+    "coma_upload_small": (C.c_int, [_vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -128,19 +128,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of `swz` bytes, 8-row groups
-// `8*swz` bytes apart (SBO), version 1 (sm_100), layout = 2 (128B) / 4 (64B) / 6 (32B swizzle).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz) {
-  const uint64_t layout = swz == 128 ? 2ull : (swz == 64 ? 4ull : 6ull);
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;                           // LBO (unused for swizzled K-major)
-  d |= (uint64_t)((8u * (uint32_t)swz) >> 4) << 32;  // SBO
-  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-  d |= layout << 61;
-  return d;
-}
-
 // ---------------------------------------------------------------------------------------------- epilogue helpers
 // y = act(cA[c] * acc + cS[c]) with cA = scale (or 1) and cS = scale*bias + shift staged in shared memory per (sample,
 // N tile); activation as hi + neg*lo (NONE: neg=1, RELU: neg=0, LEAKY/PReLU: neg=slope; clamp0 = ReLU(PReLU(.))).

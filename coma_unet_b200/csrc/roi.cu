@@ -386,3 +386,23 @@ extern "C" int coma_prepare_volumes(const coma_prepare_args* a, coma_stream_t st
   COMA_CHECK_LAUNCH("prepare_volumes");
   return COMA_OK;
 }
+
+namespace coma {
+struct SmallUpload { float v[960]; };
+__global__ void upload_small_kernel(float* __restrict__ dst, const SmallUpload s, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = s.v[i];
+}
+}  // namespace coma
+
+extern "C" int coma_upload_small(float* dst, const float* host_values, int64_t n, coma_stream_t stream) {
+  COMA_CHECK_ARG(dst && host_values && n >= 0, "coma_upload_small: bad arguments");
+  for (int64_t off = 0; off < n; off += 960) {
+    coma::SmallUpload s;
+    const int m = (int)std::min<int64_t>(960, n - off);
+    memcpy(s.v, host_values + off, (size_t)m * sizeof(float));
+    coma::upload_small_kernel<<<(m + 255) / 256, 256, 0, stream>>>(dst + off, s, m);
+    COMA_CHECK_LAUNCH("upload_small");
+  }
+  return COMA_OK;
+}

@@ -53,40 +53,40 @@ class _StaticInputs:
         self.tau = None if tau is None else torch.empty(tau.shape, dtype=torch.float32, device=dev)
         self.n_cov = covars.reshape(B, -1).shape[1]
         n_roi = len(model.roi_indices)
-        # one pinned block: [B, n_cov] covariates followed by the [B, n_roi, 2] ROI table; double-buffered so that refilling it
-        # for step i+1 never races the asynchronous upload of step i
-        self.stage = [torch.empty(B * self.n_cov + B * n_roi * 2, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.stage_done = [None, None]
+        # one block: [B, n_cov] covariates followed by the [B, n_roi, 2] ROI table, uploaded through kernel parameters
+        # (coma_upload_small): no copy engine, no pinned staging, nothing to race
+        self.stage = torch.empty(B * self.n_cov + B * n_roi * 2, dtype=torch.float32)
         self.small = torch.empty(B * self.n_cov + B * n_roi * 2, dtype=torch.float32, device=dev)
         self.covars = self.small[:B * self.n_cov].view(B, 1, self.n_cov)
         self.lut = self.small[B * self.n_cov:].view(B, n_roi, 2)
-        self.turn = 0
+
+    @staticmethod
+    def _refresh(dst, src):
+        # device -> device through an SM kernel, not cudaMemcpyAsync: a copy-engine D2D queues behind the (2.5 ms) H2D upload of
+        # the NEXT batch that a prefetcher has in flight, which serialised upload and replay (measured: 12.1 -> 14.2 ms per step)
+        if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
+            torch.mul(src, 1, out=dst)
+        else:
+            dst.copy_(src, non_blocking=True)
 
     def fill(self, model, mri, roi, tau, covars, roi_pred_dicts):
-        self.mri.copy_(mri, non_blocking=True)
-        self.roi.copy_(roi, non_blocking=True)
+        self._refresh(self.mri, mri)
+        self._refresh(self.roi, roi)
         if self.tau is not None:
-            self.tau.copy_(tau, non_blocking=True)
-        i = self.turn
-        self.turn ^= 1
-        if self.stage_done[i] is not None:
-            self.stage_done[i].synchronize()
-        st = self.stage[i]
+            self._refresh(self.tau, tau)
+        st = self.stage
         B = mri.shape[0]
-        st[:B * self.n_cov].copy_(covars.reshape(-1).to(torch.float32))
+        st[:B * self.n_cov].copy_(covars.reshape(-1).to(device="cpu", dtype=torch.float32))
         st[B * self.n_cov:].copy_(torch.from_numpy(model.roi_lut_host(roi_pred_dicts)).reshape(-1))
-        self.small.copy_(st, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self.stage_done[i] = ev
+        _lib.call("coma_upload_small", self.small.data_ptr(), st.data_ptr(), st.numel(), _lib.stream())
 
 
 class GraphedTrainStep:
     """``loss = step(mri, tau, roi, covars, roi_pred_dicts)``: one optimizer step, replayed from a CUDA graph.
 
     ``optimizer`` must be ``torch.optim.AdamW(..., fused=True, capturable=True)`` (``make_optimizer`` builds it); ``engine`` is
-    the model's ``DataParallelEngine`` (world size 1 is fine).  Returns the step's loss as a device tensor that is overwritten
-    by the next call (clone it to keep it); ``gen_loss`` holds the per-sample generative losses of the same step.
+    the model's ``DataParallelEngine`` (world size 1 is fine).  Returns the step's loss as a device tensor; ``gen_loss`` holds
+    the per-sample generative losses of the same step.
     """
 
     def __init__(self, model, criterion, optimizer, engine, warmup: int = 2):
@@ -153,7 +153,7 @@ class GraphedTrainStep:
                 self.graphs[key].replay()
                 self.replays += 1
                 _lib.launches += self.launches[key]
-                out = self.outputs[key]
+                out = tuple(t.clone() for t in self.outputs[key])      # the graph's own output buffers are rewritten by the next replay
         cur.wait_stream(self.stream)
         self.model._coma_stale_caches = True
         self.gen_loss = out[1]
@@ -182,8 +182,7 @@ class GraphedTrainStep:
 
 class GraphedInference:
     """``pred = infer(mri, covars, roi_pred_dicts, roi)``: the no-grad forward replayed from a CUDA graph (eval mode, fixed shapes).
-    The returned tensor is overwritten by the next call.  The graph holds the packed weights of the moment it was captured:
-    call ``reset()`` after the parameters change."""
+    The graph holds the packed weights of the moment it was captured: call ``reset()`` after the parameters change."""
 
     def reset(self):
         self.graph, self.out, self.seen = None, None, 0
@@ -222,6 +221,6 @@ class GraphedInference:
                     self.graph = g
                 self.graph.replay()
                 _lib.launches += self.launches
-                out = self.out
+                out = self.out.clone()       # 67 MB at batch 8: 0.02 ms; asynchronous consumers (HostSink) must not race the next replay
         cur.wait_stream(self.stream)
         return out

@@ -303,6 +303,15 @@ typedef struct {
 } coma_prepare_args;
 int coma_prepare_volumes(const coma_prepare_args* a, coma_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Small host -> device upload that does not touch a copy engine: `host_values` (n fp32 numbers in ordinary host memory: the
+ * per-batch covariates and the B x 36 x 2 ROI table the reference reads from its JSON lookups, attn_unet_data_parallel.py:
+ * 708-710,809-810) travel in the kernel parameter space, 960 values per launch.  A cudaMemcpyAsync of these ~2.5 KB queues on the
+ * H2D copy engine behind the 134 MB volume upload of the NEXT batch, which stalled the step that needs them by the whole upload
+ * (measured: +2 ms per 12 ms inference step).  The host values are consumed before the call returns.
+ * ------------------------------------------------------------------------------------------- */
+int coma_upload_small(float* dst, const float* host_values, int64_t n, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
