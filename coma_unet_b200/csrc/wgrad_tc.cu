@@ -239,6 +239,230 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+
+// =================================================================================================================================
+// Stride-2 weight gradient (the four down-sampling convs and, with the roles of x and dy swapped, the four transposed convs):
+//     dw[kd,kh,kw][cg][cx] += sum_o g[o][cg] * x[2 o + (kd-1, kh-1, kw-1)][cx]          (g on the coarse grid, x on the fine one)
+// The stride breaks the stride-1 trick of moving the kh shift onto g (o -> o + 1 moves x by two voxels), so here
+//   * the M = 128 rows of one MMA are (kh = 0, 1, 2, [unused]) x 32 x-channels: the fine lines 2 oh - 1, 2 oh, 2 oh + 1 of a
+//     slab are consecutive, so the four M chunks are one line pitch apart (LBO = line pitch, any multiple of 16 bytes is legal);
+//   * kw is the PARITY of the fine voxel: TMA element strides (2 along W) deliver every fine plane as an even slab E (fine
+//     w = 2 ow, BW rows per line) and an odd slab O (fine w = 2 ow - 1, BW + 1 rows per line); kw = 1 reads E, kw = 0 reads O
+//     from row 0, kw = 2 reads O from row 1 -- three MMAs (N = 32 gradient channels, 128 x 32 x 16: 40 cycles) per 16 coarse voxels;
+//   * kd is the parity of the fine PLANE: plane 2 od is the kd = 1 operand of coarse plane od, plane 2 od + 1 the kd = 2 operand of
+//     od and the kd = 0 operand of od + 1.  Fine planes are consumed in arrival order against one or two resident g planes,
+//     so a plane is fetched once (odd W voxels once, not twice) and only a short ring of slots is needed.
+// Nine [128 x 32] fp32 accumulators (kd, kw) live in TMEM for the CTA's life (288 columns) and leave through fp32 atomics.
+// Peak of the scheme: 96 x 32 x 16 x 2 useful FLOP per 40-cycle MMA = 690 TFLOP/s at 1.9 GHz (the mma.sync kernel it replaces
+// runs at ~130); TMA traffic 83 KB per 2880-cycle coarse plane = 29 B/clk/SM.
+template <int BW>
+struct GeoS2 {
+  static constexpr int CH = 32, ROWB = 64;
+  static constexpr int BH = 128 / BW;                           // K = 128 coarse voxels per plane: 4 x 32 or 8 x 16
+  static constexpr int L = 2 * BH + 1;                          // fine lines per plane
+  static constexpr uint32_t E_BYTES = L * BW * ROWB;            // even slab
+  static constexpr uint32_t O_RAW = L * (BW + 1) * ROWB;        // odd slab as TMA writes it
+  static constexpr uint32_t O_BYTES = (O_RAW + 1023u) & ~1023u;
+  static constexpr uint32_t F_BYTES = E_BYTES + O_BYTES;        // one fine-plane slot
+  static constexpr uint32_t G_BYTES = BH * BW * ROWB;           // one coarse plane of g
+  static constexpr int KSTEPS = 128 / 16, SEGS = BW / 16;
+  static_assert(E_BYTES % 1024 == 0 && G_BYTES % 1024 == 0, "slabs keep the swizzle phase");
+};
+constexpr int FRING = 4, GRING = 3;
+
+template <int BW>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_s2_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
+                                                                  const __grid_constant__ CUtensorMap tmG, const WgParams p) {
+  using G = GeoS2<BW>;
+  constexpr int BH = G::BH;
+  extern __shared__ uint8_t wg_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* gsm = smem + FRING * G::F_BYTES;
+  uint64_t* ffull = reinterpret_cast<uint64_t*>(gsm + GRING * G::G_BYTES + 4096);     // 4 KB that the unused M chunk may read
+  uint64_t* fempty = ffull + FRING;
+  uint64_t* gfull = fempty + FRING;
+  uint64_t* gempty = gfull + GRING;
+  uint64_t* done = gempty + GRING;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y, cg0 = (pair / p.cx_slabs) * 32, cx0 = (pair % p.cx_slabs) * 32;
+  const bool has_work = (int)blockIdx.x < p.items;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FRING; ++i) { bar_init(ffull + i, 1); bar_init(fempty + i, 1); }
+    for (int i = 0; i < GRING; ++i) { bar_init(gfull + i, 1); bar_init(gempty + i, 1); }
+    bar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: fine planes 2 d0 - 1 .. 2 (d0 + nd) - 1, g planes d0 ..
+    if (elect_lane()) {
+      uint32_t nf = 0, ng = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const Item c = decode_item<BH, BW>(p, it);
+        for (int q = 0; q <= 2 * c.nd; ++q) {
+          if ((q & 1) == 0 && (q >> 1) < c.nd) {                       // g[t] is first needed with fine plane 2 t
+            const int gs = ng % GRING;
+            bar_wait(gempty + gs, ((ng / GRING) & 1) ^ 1);
+            bar_expect_tx(gfull + gs, G::G_BYTES);
+            tma_5d(gsm + gs * G::G_BYTES, &tmG, gfull + gs, cg0, c.w0, c.h0, c.d0 + (q >> 1), c.b);
+            ++ng;
+          }
+          const int fs = nf % FRING;
+          bar_wait(fempty + fs, ((nf / FRING) & 1) ^ 1);
+          uint8_t* dst = smem + fs * G::F_BYTES;
+          bar_expect_tx(ffull + fs, G::E_BYTES + G::O_RAW);
+          const int dz = 2 * c.d0 - 1 + q;
+          tma_5d(dst, &tmE, ffull + fs, cx0, 2 * c.w0, 2 * c.h0 - 1, dz, c.b);
+          tma_5d(dst + G::E_BYTES, &tmO, ffull + fs, cx0, 2 * c.w0 - 1, 2 * c.h0 - 1, dz, c.b);
+          ++nf;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_lane()) {
+      // D f32, A / B bf16, both MN-major, N = 32, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t base = s32(smem), gbase0 = s32(gsm);
+      uint32_t nf = 0, ng0 = 0, started = 0;                           // started: bit kd set once the kd accumulators hold data
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const Item c = decode_item<BH, BW>(p, it);
+        for (int q = 0; q <= 2 * c.nd; ++q, ++nf) {
+          const int fs = nf % FRING;
+          const int t = q >> 1;
+          if ((q & 1) == 0 && t < c.nd) bar_wait(gfull + ((ng0 + t) % GRING), ((ng0 + t) / GRING) & 1);
+          bar_wait(ffull + fs, (nf / FRING) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t fbase = base + fs * G::F_BYTES;
+          // the (kd, g plane) uses of this fine plane
+          int kds[2], gts[2], nuse = 0;
+          if (q & 1) { kds[0] = 1; gts[0] = t; nuse = 1; }
+          else {
+            if (t < c.nd) { kds[nuse] = 0; gts[nuse] = t; ++nuse; }
+            if (t >= 1) { kds[nuse] = 2; gts[nuse] = t - 1; ++nuse; }
+          }
+          for (int u = 0; u < nuse; ++u) {
+            const int kd = kds[u];
+            const uint32_t gb = gbase0 + ((ng0 + gts[u]) % GRING) * G::G_BYTES;
+            const uint32_t first = (started >> kd) & 1u;
+#pragma unroll 1
+            for (int ks = 0; ks < G::KSTEPS; ++ks) {
+              const int hl = ks / G::SEGS, seg = ks % G::SEGS;
+              const uint64_t bdesc = mn_desc<64>(gb + (uint32_t)(hl * BW + seg * 16) * 64u, 64u, 512u);
+              const uint32_t acc = first | (ks > 0 ? 1u : 0u);
+              // kw = 1: even slab; kw = 0 / 2: odd slab from row 0 / row 1.  M chunks = the fine lines 2 hl, 2 hl + 1, 2 hl + 2 (kh).
+              const uint64_t a1 = mn_desc<64>(fbase + (uint32_t)((2 * hl) * BW + seg * 16) * 64u, (uint32_t)BW * 64u, 512u);
+              const uint32_t ob = fbase + G::E_BYTES + (uint32_t)((2 * hl) * (BW + 1) + seg * 16) * 64u;
+              const uint64_t a0 = mn_desc<64>(ob, (uint32_t)(BW + 1) * 64u, 512u);
+              const uint64_t a2 = mn_desc<64>(ob + 64u, (uint32_t)(BW + 1) * 64u, 512u);
+              mma_bf16_ss(tmem + (kd * 3 + 0) * 32, a0, bdesc, idesc, acc);
+              mma_bf16_ss(tmem + (kd * 3 + 1) * 32, a1, bdesc, idesc, acc);
+              mma_bf16_ss(tmem + (kd * 3 + 2) * 32, a2, bdesc, idesc, acc);
+            }
+            started |= 1u << kd;
+          }
+          commit_to(fempty + fs);
+          if ((q & 1) == 0 && t >= 1) commit_to(gempty + ((ng0 + t - 1) % GRING));      // g[t-1] has seen its kd = 0, 1, 2 planes
+        }
+        ng0 += c.nd;
+      }
+      commit_to(done);
+    }
+  } else if (has_work) {
+    // ---------------------------------------------------------------- epilogue: TMEM -> fp32 atomics into dw[tap][Cg][Cx]
+    bar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = (warp & 3) * 32 + lane;                           // TMEM lane = M row = kh * 32 + x channel
+    const int kh = m / 32, cxl = m % 32;
+#pragma unroll 1
+    for (int a = 0; a < 9; ++a) {                                   // accumulator a = kd * 3 + kw
+      const int kd = a / 3, kw = a % 3;
+      const int tap = (kd * 3 + (kh < 3 ? kh : 0)) * 3 + kw;
+      float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + cxl;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + a * 32 + part * 16, v);   // warp-collective
+        if (kh < 3) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+template <int BW>
+int launch_wgrad_s2_tc(const coma_wgrad_args& a, cudaStream_t stream) {
+  using G = GeoS2<BW>;
+  CUtensorMap tmE, tmO, tmG;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cx, (cuuint64_t)a.Wx, (cuuint64_t)a.Hx, (cuuint64_t)a.Dx, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.x_cs * 2, (cuuint64_t)a.Wx * a.x_cs * 2, (cuuint64_t)a.Hx * a.Wx * a.x_cs * 2,
+                             (cuuint64_t)a.Dx * a.Hx * a.Wx * a.x_cs * 2};
+    cuuint32_t estr[5] = {1, 2, 1, 1, 1};                       // every other fine voxel along W
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.x) + a.x_co));
+    cuuint32_t boxE[5] = {32, 2 * BW, (cuuint32_t)G::L, 1, 1};
+    cuuint32_t boxO[5] = {32, 2 * (BW + 1), (cuuint32_t)G::L, 1, 1};
+    if (!tensor_map_bf16(&tmE, base, 5, dims, strides, boxE, estr, 64)) return COMA_ERR_CUDA;
+    if (!tensor_map_bf16(&tmO, base, 5, dims, strides, boxO, estr, 64)) return COMA_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cg, (cuuint64_t)a.Wg, (cuuint64_t)a.Hg, (cuuint64_t)a.Dg, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.g_cs * 2, (cuuint64_t)a.Wg * a.g_cs * 2, (cuuint64_t)a.Hg * a.Wg * a.g_cs * 2,
+                             (cuuint64_t)a.Dg * a.Hg * a.Wg * a.g_cs * 2};
+    cuuint32_t box[5] = {32, BW, (cuuint32_t)G::BH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(a.g) + a.g_co));
+    if (!tensor_map_bf16(&tmG, base, 5, dims, strides, box, estr, 64)) return COMA_ERR_CUDA;
+  }
+  WgParams p{};
+  p.dw = a.dw;
+  p.B = a.B; p.D = a.Dg; p.H = a.Hg; p.W = a.Wg; p.Cg = a.Cg; p.Cx = a.Cx;
+  p.cg_tiles = a.Cg / 32;
+  p.cx_slabs = a.Cx / 32;
+  p.nh = a.Hg / G::BH;
+  p.nw = a.Wg / BW;
+  const int pairs = p.cg_tiles * p.cx_slabs;
+  int gx = num_sms() / pairs;
+  if (gx < 1) gx = 1;
+  p.DC = a.Dg;
+  while (p.DC > 4 && (int64_t)a.B * ((a.Dg + p.DC - 1) / p.DC) * p.nh * p.nw < (int64_t)4 * gx) p.DC = (p.DC + 1) / 2;
+  p.nd = (a.Dg + p.DC - 1) / p.DC;
+  p.items = a.B * p.nd * p.nh * p.nw;
+  if (gx > p.items) gx = p.items;
+  const size_t smem = (size_t)FRING * G::F_BYTES + (size_t)GRING * G::G_BYTES + 4096 + 1024 + 256;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(wgrad_s2_tc_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+  dim3 grid((unsigned)gx, (unsigned)pairs);
+  wgrad_s2_tc_kernel<BW><<<grid, kThreads, smem, stream>>>(tmE, tmO, tmG, p);
+  COMA_CHECK_LAUNCH("wgrad_s2_tc");
+  return COMA_OK;
+}
+
+static bool wgrad_s2_tc_ok(const coma_wgrad_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_S2_TC"); return e && e[0] == '1'; }();
+  const bool lines = (a.Wg % 32 == 0 && a.Hg % 4 == 0) || (a.Wg % 16 == 0 && a.Hg % 8 == 0);
+  return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 2 && a.pad == 1 && a.Cg % 32 == 0 && a.Cx % 32 == 0 && lines &&
+         a.Dg >= 2 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15) == 0;
+}
+
 }  // namespace
 
 namespace {
@@ -291,6 +515,7 @@ int launch_wgrad_tc(const coma_wgrad_args& a, cudaStream_t stream) {
 }  // namespace
 
 bool wgrad_tc_supported(const coma_wgrad_args& a) {
+  if (a.stride == 2) return wgrad_s2_tc_ok(a);
   static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_TC"); return e && e[0] == '1'; }();
   const bool lines = (a.Wg % 32 == 0 && a.Hg % 8 == 0) || (a.Wg == 16 && a.Hg % 16 == 0);
   return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && lines &&
@@ -299,6 +524,7 @@ bool wgrad_tc_supported(const coma_wgrad_args& a) {
 }
 
 int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  if (a.stride == 2) return a.Wg % 32 == 0 && a.Hg % 4 == 0 ? launch_wgrad_s2_tc<32>(a, stream) : launch_wgrad_s2_tc<16>(a, stream);
   const bool x32 = a.Cx % 32 == 0, g32 = a.Cg % 32 == 0, w32 = a.Wg % 32 == 0;
 #define COMA_WGTC_CASE(XV, GV, WV) if (x32 == (XV == 32) && g32 == (GV == 32) && w32 == (WV == 32)) return launch_wgrad_tc<XV, GV, WV>(a, stream);
   COMA_WGTC_CASE(32, 32, 32) COMA_WGTC_CASE(32, 16, 32) COMA_WGTC_CASE(16, 32, 32) COMA_WGTC_CASE(16, 16, 32)

@@ -78,6 +78,15 @@ CONV_CASES = [
     (1, 16, 32, 4, 8, 64, 3, 1, False),
     (2, 32, 64, 16, 16, 16, 3, 1, False),   # 16-voxel lines (the 16^3 level): 16 lines x 16 voxels per plane
     (2, 16, 1, 6, 16, 32, 3, 1, False),     # one-channel gradient padded to a 16-channel row for the tcgen05 weight gradient
+    # tcgen05 STRIDE-2 weight gradient (coarse grid W % 32 == 0, H % 4 == 0 or W % 16 == 0, H % 8 == 0; channels multiples of 32):
+    # fine planes split into even / odd W slabs by TMA element strides, kh in the M chunks, (kd, kw) in nine accumulators
+    (1, 32, 32, 6, 8, 64, 3, 2, False),     # one column, 3 coarse planes
+    (2, 32, 64, 10, 16, 64, 3, 2, False),   # two gradient tiles, several H columns, odd number of coarse planes
+    (1, 64, 32, 8, 16, 32, 3, 2, False),    # 16-voxel lines (coarse 4 x 8 x 16), two x slabs
+    (2, 64, 64, 20, 32, 32, 3, 2, False),   # depth split into chunks
+    (1, 64, 32, 5, 4, 32, 3, 2, True),      # transposed conv: x / dy swap roles (coarse = the conv-transpose INPUT)
+    (2, 32, 32, 4, 8, 16, 3, 2, True),
+    (1, 128, 64, 3, 8, 32, 3, 2, True),
 ]
 
 
