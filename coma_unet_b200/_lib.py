@@ -46,7 +46,8 @@ class WgradArgs(C.Structure):
     _fields_ = [("g", _vp), ("x", _vp), ("dw", _vp),
                 ("B", _i32), ("Dg", _i32), ("Hg", _i32), ("Wg", _i32), ("Dx", _i32), ("Hx", _i32), ("Wx", _i32),
                 ("Cg", _i32), ("Cx", _i32), ("g_cs", _i32), ("g_co", _i32), ("x_cs", _i32), ("x_co", _i32),
-                ("ksize", _i32), ("stride", _i32), ("pad", _i32), ("dtype", _i32), ("impl", _i32)]
+                ("ksize", _i32), ("stride", _i32), ("pad", _i32), ("dtype", _i32), ("impl", _i32),
+                ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
 class NormFinalizeArgs(C.Structure):
@@ -114,6 +115,7 @@ EXPORTS = {
     "coma_conv3d_tcgen05_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_impl": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_wgrad_tcgen05_supported": (C.c_int, [C.POINTER(WgradArgs)]),
+    "coma_conv3d_wgrad_workspace_size": (_i64, [C.POINTER(WgradArgs)]),
     "coma_conv3d_prologue_supported": (C.c_int, [C.POINTER(ConvArgs)]),
     "coma_conv3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "coma_convT3d_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),

@@ -22,6 +22,7 @@ int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool wgrad_mma_supported(const coma_wgrad_args& a);
 int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool wgrad_tc_supported(const coma_wgrad_args& a);
+int64_t wgrad_tc_workspace(const coma_wgrad_args& a);
 int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool conv_tc_supported(const coma_conv_args& a);
 int conv_tc_stat_chunks(const coma_conv_args& a);
@@ -94,6 +95,9 @@ extern "C" int coma_conv3d_tcgen05_supported(const coma_conv_args* a) { return a
 extern "C" int coma_conv3d_impl(const coma_conv_args* a) { return a ? pick_impl(*a) : COMA_IMPL_SIMT; }
 extern "C" int coma_conv3d_wgrad_tcgen05_supported(const coma_wgrad_args* a) {
   return a && a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a) ? 1 : 0;
+}
+extern "C" int64_t coma_conv3d_wgrad_workspace_size(const coma_wgrad_args* a) {
+  return a && a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a) ? wgrad_tc_workspace(*a) : 0;
 }
 extern "C" int coma_conv3d_prologue_supported(const coma_conv_args* a) {
   if (!a || a->transposed) return 0;

@@ -24,6 +24,7 @@
 // with fp32 atomics at the end (the same contract as the mma.sync kernels in wgrad_mma.cu).
 // Warp roles (192 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include <cuda.h>
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -54,6 +55,7 @@ constexpr int kThreads = 192;
 
 struct WgParams {
   float* dw;
+  float* ws;                                   // deterministic path: per-CTA partial blocks [gridDim.x][pairs][27][CHG][CHX], or nullptr
   int B, D, H, W, Cg, Cx;
   int cg_tiles, cx_slabs;
   int DC, nd, nh, nw, items;                    // depth chunk, chunks / columns per axis, work items per channel pair
@@ -217,18 +219,26 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int m = (warp & 3) * 32 + lane;                           // TMEM lane = M row = kw * CHX + input channel
     const int kw = m / CHX, cxl = m % CHX;
 #pragma unroll 1
+    float* wsb = p.ws ? p.ws + ((int64_t)blockIdx.x * gridDim.y + pair) * (27 * CHG * CHX) : nullptr;
+#pragma unroll 1
     for (int kd = 0; kd < 3; ++kd)
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
         const int tap = (kd * 3 + (2 - j)) * 3 + (kw < 3 ? kw : 0);
         float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + cxl;
+        float* wdst = wsb ? wsb + (int64_t)tap * (CHG * CHX) + cxl : nullptr;
 #pragma unroll
         for (int part = 0; part < CHG / 16; ++part) {
           uint32_t v[16];
           tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kd * ACC_COLS + j * CHG + part * 16, v);   // warp-collective
           if (kw < 3) {
+            if (wdst) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
+              for (int i = 0; i < 16; ++i) wdst[(part * 16 + i) * CHX] = __uint_as_float(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -239,6 +249,38 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+
+// Deterministic finish: dw[tap][cg][cx] = sum over the CTAs of a channel pair of their partial blocks, in CTA order (a plain
+// store: dw need not be zeroed).  ws: [gx][pairs][27][CHG][CHX].
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int gx, int pairs,
+                                                           int cx_slabs, int CHG, int CHX, int Cg, int Cx) {
+  // 32 elements per block; the eight 32-thread rows each sum every eighth CTA block, then row 0 adds the eight row sums in row
+  // order: a fixed association for a given grid, whatever order the CTAs finished in
+  __shared__ float part[8][32];
+  const int per = 27 * CHG * CHX;
+  const int pair = blockIdx.y;
+  const int cg0 = (pair / cx_slabs) * CHG, cx0 = (pair % cx_slabs) * CHX;
+  const int row = threadIdx.x >> 5, e = blockIdx.x * 32 + (threadIdx.x & 31);
+  float s = 0.f;
+  if (e < per)
+    for (int c = row; c < gx; c += 8) s += ws[((int64_t)c * pairs + pair) * per + e];
+  part[row][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (row == 0 && e < per) {
+    float t = part[0][threadIdx.x];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += part[r][threadIdx.x];
+    const int tap = e / (CHG * CHX), r2 = e % (CHG * CHX);
+    dw[((int64_t)tap * Cg + cg0 + r2 / CHX) * Cx + cx0 + r2 % CHX] = t;
+  }
+}
+
+static int wgrad_finish(const WgParams& p, const coma_wgrad_args& a, int gx, int pairs, int CHG, int CHX, cudaStream_t stream) {
+  dim3 grid((unsigned)((27 * CHG * CHX + 31) / 32), (unsigned)pairs);
+  wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, p.dw, gx, pairs, p.cx_slabs, CHG, CHX, a.Cg, a.Cx);
+  COMA_CHECK_LAUNCH("wgrad_finish");
+  return COMA_OK;
+}
 
 // =================================================================================================================================
 // Stride-2 weight gradient (the four down-sampling convs and, with the roles of x and dy swapped, the four transposed convs):
@@ -385,18 +427,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_s2_tc_kernel(const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = (warp & 3) * 32 + lane;                           // TMEM lane = M row = kh * 32 + x channel
     const int kh = m / 32, cxl = m % 32;
+    float* wsb = p.ws ? p.ws + ((int64_t)blockIdx.x * gridDim.y + pair) * (27 * 32 * 32) : nullptr;
 #pragma unroll 1
     for (int a = 0; a < 9; ++a) {                                   // accumulator a = kd * 3 + kw
       const int kd = a / 3, kw = a % 3;
       const int tap = (kd * 3 + (kh < 3 ? kh : 0)) * 3 + kw;
       float* dst = p.dw + ((int64_t)tap * p.Cg + cg0) * p.Cx + cx0 + cxl;
+      float* wdst = wsb ? wsb + (int64_t)tap * (32 * 32) + cxl : nullptr;
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         uint32_t v[16];
         tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + a * 32 + part * 16, v);   // warp-collective
         if (kh < 3) {
+          if (wdst) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) wdst[(part * 16 + i) * 32] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)(part * 16 + i) * p.Cx, __uint_as_float(v[i]));
+          }
         }
       }
     }
@@ -450,8 +499,10 @@ int launch_wgrad_s2_tc(const coma_wgrad_args& a, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(wgrad_s2_tc_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   dim3 grid((unsigned)gx, (unsigned)pairs);
+  p.ws = (a.workspace && a.workspace_bytes >= (int64_t)gx * pairs * 27 * 32 * 32 * 4) ? static_cast<float*>(a.workspace) : nullptr;
   wgrad_s2_tc_kernel<BW><<<grid, kThreads, smem, stream>>>(tmE, tmO, tmG, p);
   COMA_CHECK_LAUNCH("wgrad_s2_tc");
+  if (p.ws) return wgrad_finish(p, a, gx, pairs, 32, 32, stream);
   return COMA_OK;
 }
 
@@ -508,8 +559,10 @@ int launch_wgrad_tc(const coma_wgrad_args& a, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(wgrad_tc_kernel<CHX, CHG, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   dim3 grid((unsigned)gx, (unsigned)pairs);
+  p.ws = (a.workspace && a.workspace_bytes >= (int64_t)gx * pairs * 27 * CHG * CHX * 4) ? static_cast<float*>(a.workspace) : nullptr;
   wgrad_tc_kernel<CHX, CHG, BW><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   COMA_CHECK_LAUNCH("wgrad_tc");
+  if (p.ws) return wgrad_finish(p, a, gx, pairs, CHG, CHX, stream);
   return COMA_OK;
 }
 }  // namespace
@@ -521,6 +574,14 @@ bool wgrad_tc_supported(const coma_wgrad_args& a) {
   return !off && a.dtype == COMA_BF16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Cg % 16 == 0 && a.Cx % 16 == 0 && lines &&
          a.Dg >= 4 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 &&
          ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15) == 0;
+}
+
+int64_t wgrad_tc_workspace(const coma_wgrad_args& a) {
+  // one [27][CHG][CHX] block per CTA; gx * pairs <= max(#SMs, pairs)
+  const int chg = a.stride == 2 ? 32 : (a.Cg % 32 == 0 ? 32 : 16), chx = a.stride == 2 ? 32 : (a.Cx % 32 == 0 ? 32 : 16);
+  const int64_t pairs = (int64_t)(a.Cg / chg) * (a.Cx / chx);
+  const int64_t ctas = std::max<int64_t>(num_sms(), pairs);
+  return ctas * 27 * chg * chx * 4;
 }
 
 int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream) {

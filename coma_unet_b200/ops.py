@@ -231,6 +231,7 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
     return y, stats
 
 
+DETERMINISTIC_WGRAD = os.environ.get("COMA_WGRAD_ATOMICS", "0") != "1"     # A/B switch: fp32 atomics into a zeroed dw instead
 _CG1_SIMT = os.environ.get("COMA_CG1_SIMT", "0") == "1"     # A/B switch: keep one-channel weight gradients on the CUDA-core sweep
 
 
@@ -245,13 +246,21 @@ def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad", alg=None):
         # zero-padded to one 16-channel row it runs on the tcgen05 weight-gradient kernel (0.1 ms pad + 0.3 ms)
         g16 = torch.nn.functional.pad(g, (0, 15))
         return wgrad_raw(g16, x, ksize=ksize, stride=stride, kind=kind, alg=alg or (1, Cx))[:, :1, :].contiguous()
-    dw = torch.zeros(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
     a = L.WgradArgs()
-    a.g, a.x, a.dw = L.ptr(g), L.ptr(x), L.ptr(dw)
+    a.g, a.x = L.ptr(g), L.ptr(x)
     a.B, a.Dg, a.Hg, a.Wg, a.Dx, a.Hx, a.Wx = B, Dg, Hg, Wg, Dx, Hx, Wx
     a.Cg, a.Cx, a.g_cs, a.g_co, a.x_cs, a.x_co = Cg, Cx, vol_cs(g), 0, vol_cs(x), 0
     a.ksize, a.stride, a.pad, a.dtype, a.impl = ksize, stride, (ksize - 1) // 2, L.dtype_code(g.dtype), L.IMPL_AUTO
     a.alg = alg if alg is not None else (Cg, Cx)       # layer channel counts without padding (see _conv_args)
+    ws_bytes = L.lib().coma_conv3d_wgrad_workspace_size(C.byref(a)) if DETERMINISTIC_WGRAD else 0
+    if ws_bytes > 0:
+        # tcgen05 kernels, deterministic finish: per-CTA partial blocks summed in a fixed order and stored (no zero fill, no atomics)
+        ws = torch.empty(ws_bytes, device=g.device, dtype=torch.uint8)
+        dw = torch.empty(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
+        a.workspace, a.workspace_bytes = L.ptr(ws), ws_bytes
+    else:
+        dw = torch.zeros(ksize ** 3, Cg, Cx, device=g.device, dtype=torch.float32)
+    a.dw = L.ptr(dw)
     L.call(kind, C.byref(a), L.stream())
     return dw
 

@@ -114,9 +114,17 @@ typedef struct {
   int32_t ksize, stride, pad;
   int32_t dtype;
   int32_t impl;
+  /* Optional (NULL / 0 = off): caller-owned scratch of at least coma_conv3d_wgrad_workspace_size() bytes.  With it the tcgen05
+   * kernels write one partial [27][Cg][Cx] block per CTA and a second kernel sums the blocks in a fixed order and STORES dw
+   * (dw need not be zeroed): bit-identical results from run to run.  Without it the CTAs add into a zeroed dw with fp32 atomics
+   * (order-dependent low bits). */
+  void* workspace; int64_t workspace_bytes;
 } coma_wgrad_args;
-/* 1 if the tcgen05 weight-gradient kernel takes this problem (bf16, k3 s1, channels multiples of 16, W % 32 == 0 or W == 16) */
+/* 1 if a tcgen05 weight-gradient kernel takes this problem: bf16, k3, and either stride 1 (channels multiples of 16, W % 32 == 0
+ * or W == 16) or stride 2 (channels multiples of 32, coarse W % 32 == 0 && H % 4 == 0 or W % 16 == 0 && H % 8 == 0) */
 int coma_conv3d_wgrad_tcgen05_supported(const coma_wgrad_args* a);
+/* bytes of scratch the deterministic path of coma_conv3d_wgrad / coma_convT3d_wgrad wants for this problem (0: no such path) */
+int64_t coma_conv3d_wgrad_workspace_size(const coma_wgrad_args* a);
 int coma_conv3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
 int coma_convT3d_wgrad(const coma_wgrad_args* a, coma_stream_t stream);
 

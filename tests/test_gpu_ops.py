@@ -631,6 +631,21 @@ def test_warp_specialised_convs_are_run_to_run_identical(case):
         assert torch.equal(y, y0) and torch.equal(st.sum(dim=1), s0)
 
 
+@pytest.mark.parametrize("case", [(4, 32, 64, 128, 1), (4, 16, 16, 128, 1), (4, 64, 32, 64, 2), (4, 256, 128, 16, 2)])
+def test_tcgen05_weight_gradients_are_bit_identical_from_run_to_run(case):
+    """the tcgen05 weight gradients no longer drain through fp32 atomics -- every CTA writes its partial
+    [27][Cg][Cx] block to the caller's workspace and a second kernel sums the blocks in CTA order (coma_wgrad_args.workspace), so
+    repeated launches at the benchmark size give bit-identical gradients (stride 1 and the stride-2 kernel)."""
+    B, Cg, Cx, Dg, s = case
+    g = rnd(B, Dg, Dg, Dg, Cg, seed=83).bfloat16()
+    x = rnd(B, Dg * s, Dg * s, Dg * s, Cx, seed=84).bfloat16()
+    assert ops.DETERMINISTIC_WGRAD
+    first = ops.wgrad_raw(g, x, ksize=3, stride=s).clone()
+    assert float(first.abs().max()) > 0
+    for _ in range(8):
+        assert torch.equal(ops.wgrad_raw(g, x, ksize=3, stride=s), first)
+
+
 # ---- input preparation (SURVEY 8f rank 4): coma_prepare_volumes against oracle/prepare.py, bit for bit ----
 @pytest.mark.parametrize("shape,spacing,pad_dims,resize", [
     ((24, 30, 20), (1.0, 1.0, 1.0), (16, 16, 16), True),      # 1 mm -> 2 mm, centred padding, odd pads
