@@ -222,7 +222,7 @@ class Convolution(nn.Module):
                 ops._copy_channels(y, out)
                 return out
             return y
-        ncfg = ops.NormCfg(mode=mode, act=code, eps=eps, stats=stats, out=None if grad else out)
+        ncfg = ops.NormCfg(mode=mode, act=code, eps=eps, stats=stats, out=out)
         if defer and not grad and out is None and mode == L.NORM_INSTANCE and code in (L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY):
             A, S, _, _, _ = ops.norm_coefficients(y, g, h, ncfg)
             sl = None if slope is None else slope.detach().float().reshape(-1)[:1].contiguous()
@@ -234,10 +234,7 @@ class Convolution(nn.Module):
             ncfg.n_updates = _bn_updates
             if ncfg.update_running:
                 norm.num_batches_tracked += _bn_updates
-        y = ops.norm_act(y, g, h, slope, ncfg)
-        if grad and out is not None:
-            raise RuntimeError("in-place output targets are only used without autograd")
-        return y
+        return ops.norm_act(y, g, h, slope, ncfg)
 
     def _packed(self, x):
         cin_buf = x.shape[-1]
@@ -343,9 +340,7 @@ class AttentionBlock(nn.Module):
         s = self._bn(tx, sx, self.W_x[1], L.ACT_RELU, residual=u)
         q, sq = ops.conv3d(s, cp.weight, cp.bias, ops.ConvCfg(**k1))
         p = self._bn(q, sq, self.psi[1], L.ACT_SIGMOID)
-        y = ops.bcast_mul(x, p, None if grad else out)
-        if grad and out is not None:
-            raise RuntimeError("in-place output targets are only used without autograd")
+        y = ops.bcast_mul(x, p, out)
         return (y, p) if want_coeff else y
 
 

@@ -89,19 +89,16 @@ class AttentionLayer(blocks.AttentionLayer):
             encs, decs = [x_sub], []
         Cn = x.shape[-1]
         grad = torch.is_grad_enabled() and (x.requires_grad or x_sub.requires_grad or self.merge.conv.weight.requires_grad)
-        if not grad:
-            # one concat buffer written in place: [att | fromlower]  (replaces torch.cat, :229)
-            cat = x.new_empty(*x.shape[:-1], 2 * Cn)
-            fromlower = self.upconv(x_sub, covariate, out=cat[..., Cn:])
-            att = self.attention(g=fromlower, x=x, out=cat[..., :Cn])
-        else:
-            fromlower = self.upconv(x_sub, covariate)
-            att = self.attention(g=fromlower, x=x)
+        # one concat buffer written in place by its two producers: [att | fromlower]  (replaces torch.cat, :229) -- with autograd
+        # too: ops.JoinFn hands the buffer to the merge conv and splits its gradient into two channel-sliced views
+        cat = x.new_empty(*x.shape[:-1], 2 * Cn)
+        fromlower = self.upconv(x_sub, covariate, out=cat[..., Cn:])
+        att = self.attention(g=fromlower, x=x, out=cat[..., :Cn])
         if self.save_attn is not None:
             att, coeff = att
             save_attention_coeffs(self.save_attn, coeff)
         if grad:
-            cat = ops.concat2(att, fromlower)
+            cat = ops.JoinFn.apply(att, fromlower, cat)
         att_m = self.merge(cat, defer=defer_out and not grad)
         return att_m, [x] + encs, [att_m] + decs
 

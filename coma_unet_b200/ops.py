@@ -460,6 +460,8 @@ class NormActFn(torch.autograd.Function):
         A, S, mean, rstd, gd = norm_coefficients(x, g, h, cfg)
         sl = None if slope is None else slope.detach().float().reshape(-1)[:1].contiguous()
         y = affine_act(x, A, S, sl, cfg.act, out=cfg.out, residual=residual)
+        if cfg.out is not None:
+            y = alias(y)               # the caller's slice of a wider (concat) buffer: not a view in autograd's eyes
         ctx.save_for_backward(x, A, S, mean, rstd, gd, sl, residual)
         ctx.cfg = cfg
         ctx.g_shape = None if g is None else g.shape
@@ -510,8 +512,33 @@ def norm_act(x, g, h, slope, cfg: NormCfg, residual=None):
 
 
 def concat2(a, b):
-    """torch.cat((a, b), channel) as two strided identity sweeps of the apply kernel (training path)."""
+    """torch.cat((a, b), channel) as two strided identity sweeps of the apply kernel (generic fallback)."""
     return Concat2Fn.apply(a, b)
+
+
+def alias(t: torch.Tensor) -> torch.Tensor:
+    """A new tensor object over the same memory that autograd does not regard as a view of anything: what a custom Function
+    returns when its kernel wrote straight into a caller-provided slice of a wider buffer."""
+    return torch.empty(0, device=t.device, dtype=t.dtype).set_(t.untyped_storage(), t.storage_offset(), t.size(), t.stride())
+
+
+class JoinFn(torch.autograd.Function):
+    """torch.cat((a, b), channel) WITHOUT a copy (attn_unet_data_parallel.py:229): ``a`` and ``b`` already are the two
+    channel halves of ``buf`` (their producers wrote them there); forward hands out ``buf``, backward hands each producer its
+    half of the gradient as a channel-sliced view (every backward kernel takes a channel stride)."""
+
+    @staticmethod
+    def forward(ctx, a, b, buf):
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        assert buf.shape[-1] == Ca + Cb and a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf[..., Ca:].data_ptr()
+        ctx.split = (Ca, Cb)
+        return alias(buf)
+
+    @staticmethod
+    def backward(ctx, d):
+        Ca, Cb = ctx.split
+        d = as_vol(d)
+        return (d[..., :Ca] if ctx.needs_input_grad[0] else None), (d[..., Ca:] if ctx.needs_input_grad[1] else None), None
 
 
 class Concat2Fn(torch.autograd.Function):
@@ -580,7 +607,7 @@ class BcastMulFn(torch.autograd.Function):
         a.x_cs, a.x_co, a.out_cs, a.out_co, a.dtype = vol_cs(x), 0, vol_cs(o), 0, L.dtype_code(x.dtype)
         L.call("coma_gate_apply_fwd", C.byref(a), L.stream())
         ctx.save_for_backward(x, p)
-        return o
+        return alias(o) if out is not None else o
 
     @staticmethod
     def backward(ctx, dout):
