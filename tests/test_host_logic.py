@@ -111,3 +111,37 @@ def test_prepare_geometry_follows_the_reference_padding_rules():
     assert res == [128, 100, 100] and out == res and before == [0, 0, 0]                                           # z matches: no transform
     res, out, _, ratio = prepare_geometry((64, 64, 64), (1.0, 1.0, 1.0), resize=False, pad_dims=None)
     assert res == [64, 64, 64] and out == res and ratio == [1.0, 1.0, 1.0]
+
+
+def test_packed_weight_cache_follows_the_weight_epoch():
+    """Fused optimizers update parameters in place without bumping ``_version`` (round-2 finding): the packed-weight cache is
+    keyed by the weight epoch as well, which every training-mode forward and every train()/eval() switch bumps."""
+    w = torch.nn.Parameter(torch.arange(2 * 3 * 27, dtype=torch.float32).reshape(2, 3, 3, 3, 3))
+    p0 = ops.pack_weight(w, False, 3, 2, torch.float32)
+    assert ops.pack_weight(w, False, 3, 2, torch.float32) is p0                 # cached
+    w.data.mul_(2.0)                                                               # what a fused optimizer step looks like: no version bump
+    assert ops.pack_weight(w, False, 3, 2, torch.float32) is p0                 # version-only key: stale by construction ...
+    ops.bump_weight_epoch()
+    p1 = ops.pack_weight(w, False, 3, 2, torch.float32)                         # ... the epoch refreshes it
+    assert p1 is not p0 and torch.equal(p1, 2 * p0)
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5, conditional=True,
+                                       prompt_shape=(16, 16, 16))
+    e0 = ops.weight_epoch()
+    m.train(True)
+    m.eval()
+    m.set_training(False)
+    assert ops.weight_epoch() >= e0 + 3
+    ops.invalidate_weight_caches(m)
+    assert ops.weight_epoch() > e0 + 3
+
+
+def test_roi_table_and_prompt_declarations():
+    m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, [8, 16, 32, 64, 128], [2] * 5, latent_spaces=[2048] * 5, conditional=True,
+                                       prompt_shape=(16, 16, 16))
+    _, _, _, _, dicts = common.synthetic_batch(2, (16, 16, 16), 3)
+    dicts[1][m.roi_names[4]]["loc"] = float("nan")
+    lut = m.roi_lut_host(dicts)
+    assert lut.shape == (2, 36, 2) and lut.dtype.name == "float32"
+    assert lut[0, 0, 0] == pytest.approx(dicts[0][m.roi_names[0]]["loc"]) and lut[1, 4, 0] == 0.0      # nan_to_num, :641
+    dd = m.data_dependent_parameters()
+    assert len(dd) == 2 and dd[0] is m.pos_dynamic_prompt and dd[1] is m.neg_dynamic_prompt
