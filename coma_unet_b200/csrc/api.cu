@@ -23,6 +23,9 @@ bool wgrad_mma_supported(const coma_wgrad_args& a);
 int wgrad_mma_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool wgrad_tc_supported(const coma_wgrad_args& a);
 int64_t wgrad_tc_workspace(const coma_wgrad_args& a);
+bool wgrad_c1k3_supported(const coma_wgrad_args& a);
+int64_t wgrad_c1k3_workspace(const coma_wgrad_args& a);
+int wgrad_c1k3_launch(const coma_wgrad_args& a, cudaStream_t stream);
 int wgrad_tc_launch(const coma_wgrad_args& a, cudaStream_t stream);
 bool conv_tc_supported(const coma_conv_args& a);
 int conv_tc_stat_chunks(const coma_conv_args& a);
@@ -97,7 +100,10 @@ extern "C" int coma_conv3d_wgrad_tcgen05_supported(const coma_wgrad_args* a) {
   return a && a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a) ? 1 : 0;
 }
 extern "C" int64_t coma_conv3d_wgrad_workspace_size(const coma_wgrad_args* a) {
-  return a && a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a) ? wgrad_tc_workspace(*a) : 0;
+  if (!a || a->impl == COMA_IMPL_SIMT) return 0;
+  if (wgrad_tc_supported(*a)) return wgrad_tc_workspace(*a);
+  if (wgrad_c1k3_supported(*a)) return wgrad_c1k3_workspace(*a);
+  return 0;
 }
 extern "C" int coma_conv3d_prologue_supported(const coma_conv_args* a) {
   if (!a || a->transposed) return 0;
@@ -133,7 +139,8 @@ static int check_wgrad(const coma_wgrad_args* a, const char* who) {
   return COMA_OK;
 }
 static int run_wgrad(const coma_wgrad_args* a, cudaStream_t stream) {
-  if (a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a)) return wgrad_tc_launch(*a, stream);      // tcgen05 (k3 s1, 32-channel multiples)
+  if (a->impl != COMA_IMPL_SIMT && wgrad_tc_supported(*a)) return wgrad_tc_launch(*a, stream);      // tcgen05 (k3, stride 1 / 2)
+  if (a->impl != COMA_IMPL_SIMT && wgrad_c1k3_supported(*a)) return wgrad_c1k3_launch(*a, stream);  // one-channel gradient, k3 s1
   if (a->impl != COMA_IMPL_SIMT && wgrad_mma_supported(*a)) return wgrad_mma_launch(*a, stream);
   return wgrad_simt_launch(*a, stream);
 }

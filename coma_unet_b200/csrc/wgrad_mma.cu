@@ -529,6 +529,157 @@ int launch_wgrad_pw(const coma_wgrad_args& a, cudaStream_t stream) {
 }
 }  // namespace
 
+
+// ---- one-channel gradient, 3x3x3, stride 1 (the 16 -> 1 / 8 -> 1 heads of the modulator stacks, attn_unet_data_parallel.py:495-497) ----
+//     dw[tap][0][cx] = sum_u x[u][cx] * g[u - (tap - 1)]
+// HBM-bound by nature (x: 32 B per voxel, g: 2 B), but 27 x 16 FMA per voxel is too much for the CUDA cores at that rate and
+// zero-padding g to a 16-channel row for the tcgen05 kernel cost 0.45 ms per layer (pad + 16-row instance) for 0.05 ms of traffic.
+// Here M = 27 taps (two m16 tiles), N = 16 x-channels (two n8 tiles), K = voxels: the B fragments come straight from the x tile
+// (rows = voxels, ldmatrix.trans), the A fragments are GATHERED from a three-plane halo tile of the scalar field g.
+// A block owns 8 lines x 32 voxels of a plane (one line per warp, two k16 steps) and marches along depth.
+namespace {
+constexpr int C1_BH = 8, C1_BW = 32, C1_HP = C1_BH + 2, C1_WP = C1_BW + 2;
+
+__global__ void __launch_bounds__(256) wgrad_c1k3_kernel(coma_wgrad_args a, int DC, int nbd, int nbh, int nbw, float* __restrict__ ws) {
+  __shared__ __align__(16) __nv_bfloat16 xs[C1_BH * C1_BW * 16];      // [line][voxel][16 ch]: 32-byte rows
+  __shared__ __nv_bfloat16 gs[3 * C1_HP * C1_WP];                      // g planes d-1, d, d+1 with an H / W halo
+  __shared__ float red[8][32 * 16];
+  int it = blockIdx.x;
+  const int wb = it % nbw; it /= nbw;
+  const int hb = it % nbh; it /= nbh;
+  const int db = it % nbd; it /= nbd;
+  const int b = it;
+  const int d0 = db * DC, d1 = min(d0 + DC, a.Dg), h0 = hb * C1_BH, w0 = wb * C1_BW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* xg = static_cast<const __nv_bfloat16*>(a.x) + a.x_co;
+  const __nv_bfloat16* gg = static_cast<const __nv_bfloat16*>(a.g) + a.g_co;
+  const int64_t plane = (int64_t)a.Hg * a.Wg;
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  // tap offsets of this thread's four A rows (m = lane / 4 + {0, 8} in each of the two m16 tiles); taps >= 27 read tap 26 and are dropped
+  int goff[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int tap = (r >> 1) * 16 + (r & 1) * 8 + (lane >> 2);
+    tap = tap < 27 ? tap : 26;
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    // g[u - (k - 1)]: plane (2 - kd), line + (2 - kh), column + (2 - kw) inside the halo tile (u itself sits at +1, +1)
+    goff[r] = ((2 - kd) * C1_HP + (2 - kh)) * C1_WP + (2 - kw);
+  }
+  for (int d = d0; d < d1; ++d) {
+    __syncthreads();
+    // x tile: 8 lines x 32 voxels x 32 bytes = 512 16-byte vectors
+    for (int v = tid; v < C1_BH * C1_BW * 2; v += 256) {
+      const int line = v / (C1_BW * 2), rem = v % (C1_BW * 2), vox = rem >> 1, half = rem & 1;
+      const int64_t gi = (((int64_t)b * a.Dx + d) * a.Hx + h0 + line) * a.Wx + w0 + vox;
+      *reinterpret_cast<uint4*>(&xs[(line * C1_BW + vox) * 16 + half * 8]) = __ldg(reinterpret_cast<const uint4*>(xg + gi * a.x_cs + half * 8));
+    }
+    for (int e = tid; e < 3 * C1_HP * C1_WP; e += 256) {
+      const int pz = e / (C1_HP * C1_WP), r = e % (C1_HP * C1_WP), py = r / C1_WP, px = r % C1_WP;
+      const int dz = d - 1 + pz, hy = h0 - 1 + py, wx = w0 - 1 + px;
+      const bool in = dz >= 0 && dz < a.Dg && hy >= 0 && hy < a.Hg && wx >= 0 && wx < a.Wg;
+      gs[e] = in ? gg[(((int64_t)b * a.Dg + dz) * plane + (int64_t)hy * a.Wg + wx) * a.g_cs] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    const unsigned short* g16 = reinterpret_cast<const unsigned short*>(gs);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // B fragments: x[k = voxel][n = cx], two n8 tiles; rows of 32 bytes, matrices 8 voxels x 8 channels
+      uint32_t bfr[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const __nv_bfloat16* p = &xs[(warp * C1_BW + ks * 16 + (lane & 15)) * 16 + nt * 8];
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(bfr[nt][0]), "=r"(bfr[nt][1]) : "r"(sa));
+      }
+      // A fragments: a0 = (row m, k 2c..2c+1), a1 = (row m+8, same k), a2 = (row m, k+8..), a3 = (row m+8, k+8..); c = lane % 4
+      const int kbase = warp * C1_WP + ks * 16 + (lane & 3) * 2;        // line `warp`, column of voxel k inside the halo tile (before +off)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t af[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int o = goff[mt * 2 + (q & 1)] + kbase + (q >> 1) * 8;
+          af[q] = (uint32_t)g16[o] | ((uint32_t)g16[o + 1] << 16);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) mma_bf16(acc[mt][nt], af, bfr[nt][0], bfr[nt][1]);
+      }
+    }
+  }
+  // block reduction over the eight warps, then one partial block [27][16] per CTA (deterministic finish) or atomics
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = mt * 16 + (lane >> 2) + (q >> 1) * 8, n = nt * 8 + (lane & 3) * 2 + (q & 1);
+        red[warp][m * 16 + n] = acc[mt][nt][q];
+      }
+  __syncthreads();
+  for (int e = tid; e < 27 * 16; e += 256) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s2 += red[w][e];
+    if (ws) ws[(int64_t)blockIdx.x * (27 * 16) + e] = s2;
+    else atomicAdd(a.dw + e, s2);
+  }
+}
+
+// sum the per-CTA blocks in CTA order (eight interleaved partial sums, then a fixed-order combine) and store dw
+__global__ void __launch_bounds__(256) wgrad_c1k3_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nblocks) {
+  __shared__ float part[8][32];
+  const int row = threadIdx.x >> 5, e = blockIdx.x * 32 + (threadIdx.x & 31);
+  float s2 = 0.f;
+  if (e < 27 * 16)
+    for (int c = row; c < nblocks; c += 8) s2 += ws[(int64_t)c * (27 * 16) + e];
+  part[row][threadIdx.x & 31] = s2;
+  __syncthreads();
+  if (row == 0 && e < 27 * 16) {
+    float t = part[0][threadIdx.x];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += part[r][threadIdx.x];
+    dw[e] = t;
+  }
+}
+
+struct C1Plan { int DC, nbd, nbh, nbw; int64_t blocks; };
+C1Plan plan_c1k3(const coma_wgrad_args& a) {
+  C1Plan p;
+  p.nbh = a.Hg / C1_BH; p.nbw = a.Wg / C1_BW;
+  p.DC = a.Dg;
+  while (p.DC > 8 && (int64_t)a.B * ((a.Dg + p.DC - 1) / p.DC) * p.nbh * p.nbw < (int64_t)8 * num_sms()) p.DC = (p.DC + 1) / 2;
+  p.nbd = (a.Dg + p.DC - 1) / p.DC;
+  p.blocks = (int64_t)a.B * p.nbd * p.nbh * p.nbw;
+  return p;
+}
+}  // namespace
+
+bool wgrad_c1k3_supported(const coma_wgrad_args& a) {
+  static const bool off = [] { const char* e = getenv("COMA_DISABLE_WGRAD_C1K3"); return e && e[0] == '1'; }();
+  return !off && a.dtype == COMA_BF16 && a.Cg == 1 && a.Cx == 16 && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.Hg % C1_BH == 0 &&
+         a.Wg % C1_BW == 0 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+}
+int64_t wgrad_c1k3_workspace(const coma_wgrad_args& a) { return plan_c1k3(a).blocks * 27 * 16 * 4; }
+int wgrad_c1k3_launch(const coma_wgrad_args& a, cudaStream_t stream) {
+  const C1Plan p = plan_c1k3(a);
+  float* ws = (a.workspace && a.workspace_bytes >= p.blocks * 27 * 16 * 4) ? static_cast<float*>(a.workspace) : nullptr;
+  wgrad_c1k3_kernel<<<(unsigned)p.blocks, 256, 0, stream>>>(a, p.DC, p.nbd, p.nbh, p.nbw, ws);
+  COMA_CHECK_LAUNCH("wgrad_c1k3");
+  if (ws) {
+    wgrad_c1k3_finish_kernel<<<(27 * 16 + 31) / 32, 256, 0, stream>>>(ws, a.dw, (int)p.blocks);
+    COMA_CHECK_LAUNCH("wgrad_c1k3_finish");
+  }
+  return COMA_OK;
+}
+
 bool wgrad_mma_supported(const coma_wgrad_args& a) {
   return a.dtype == COMA_BF16 && a.Cg % 8 == 0 && a.Cx % 8 == 0 && a.g_cs % 8 == 0 && a.g_co % 8 == 0 && a.x_cs % 8 == 0 &&
          a.x_co % 8 == 0 && (reinterpret_cast<uintptr_t>(a.g) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;

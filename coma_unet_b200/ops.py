@@ -232,6 +232,7 @@ def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None,
 
 
 DETERMINISTIC_WGRAD = os.environ.get("COMA_WGRAD_ATOMICS", "0") != "1"     # A/B switch: fp32 atomics into a zeroed dw instead
+_CG1_PAD = os.environ.get("COMA_CG1_PAD", "0") == "1"       # A/B switch: one-channel k3 weight gradients zero-padded to the tcgen05 16-row instance
 _CG1_SIMT = os.environ.get("COMA_CG1_SIMT", "0") == "1"     # A/B switch: keep one-channel weight gradients on the CUDA-core sweep
 
 
@@ -241,6 +242,7 @@ def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad", alg=None):
     B, Dg, Hg, Wg, Cg = g.shape
     _, Dx, Hx, Wx, Cx = x.shape
     if (Cg == 1 and ksize == 3 and stride == 1 and g.dtype == torch.bfloat16 and Cx % 16 == 0 and not _CG1_SIMT
+            and not (Cx == 16 and Wg % 32 == 0 and Hg % 8 == 0 and not _CG1_PAD)       # the gathered-A mma.sync kernel takes these
             and ((Wg % 32 == 0 and Hg % 8 == 0) or (Wg == 16 and Hg % 16 == 0)) and Dg >= 4):
         # one-channel gradient (the 16 -> 1 modulator heads): the CUDA-core sweep is latency-bound (1.1 ms for 0.3 GB at batch 4);
         # zero-padded to one 16-channel row it runs on the tcgen05 weight-gradient kernel (0.1 ms pad + 0.3 ms)

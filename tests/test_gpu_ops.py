@@ -87,6 +87,9 @@ CONV_CASES = [
     (1, 64, 32, 5, 4, 32, 3, 2, True),      # transposed conv: x / dy swap roles (coarse = the conv-transpose INPUT)
     (2, 32, 32, 4, 8, 16, 3, 2, True),
     (1, 128, 64, 3, 8, 32, 3, 2, True),
+    # one-channel k3 weight gradient on mma.sync with gathered A fragments (Cx = 16, W % 32 == 0, H % 8 == 0)
+    (2, 16, 1, 5, 8, 32, 3, 1, False),
+    (1, 16, 1, 20, 24, 64, 3, 1, False),    # several blocks in every dim, depth chunks
 ]
 
 
@@ -631,7 +634,7 @@ def test_warp_specialised_convs_are_run_to_run_identical(case):
         assert torch.equal(y, y0) and torch.equal(st.sum(dim=1), s0)
 
 
-@pytest.mark.parametrize("case", [(4, 32, 64, 128, 1), (4, 16, 16, 128, 1), (4, 64, 32, 64, 2), (4, 256, 128, 16, 2)])
+@pytest.mark.parametrize("case", [(4, 32, 64, 128, 1), (4, 16, 16, 128, 1), (4, 64, 32, 64, 2), (4, 256, 128, 16, 2), (4, 1, 16, 128, 1)])
 def test_tcgen05_weight_gradients_are_bit_identical_from_run_to_run(case):
     """the tcgen05 weight gradients no longer drain through fp32 atomics -- every CTA writes its partial
     [27][Cg][Cx] block to the caller's workspace and a second kernel sums the blocks in CTA order (coma_wgrad_args.workspace), so
