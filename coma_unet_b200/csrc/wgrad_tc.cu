@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_s2_tc_kernel(const __grid_c
             const int kd = kds[u];
             const uint32_t gb = gbase0 + ((ng0 + gts[u]) % GRING) * G::G_BYTES;
             const uint32_t first = (started >> kd) & 1u;
-#pragma unroll
+#pragma unroll 1
             for (int ks = 0; ks < G::KSTEPS; ++ks) {
               const int hl = ks / G::SEGS, seg = ks % G::SEGS;
               const uint64_t bdesc = mn_desc<64>(gb + (uint32_t)(hl * BW + seg * 16) * 64u, 64u, 512u);
