@@ -538,6 +538,63 @@ def test_c4_inference_volume_160x192x160_matches_oracle():
     assert mean_ours < max(3e-3, 1.5 * mean_auto), (mean_ours, mean_auto)
 
 
+def test_c5_256_crops_mixed_covariate_batch_equals_single_samples():
+    """BASELINE configs C5: 256^3 crops, full channel widths, a batch that mixes an ADNI-shaped sample (float32
+    covariates, VolumeDataset.py:427) with an A4-shaped one (float64, VolumeDataset_ADNI_A4_combined.py:86).  At this size a
+    batch-2 tensor has more than 2^31 elements, so the check is a size-independent property: with BatchNorm on its running
+    statistics the samples are independent, hence prediction and gradients of the batch must equal those of the two samples run
+    alone, and the covariate dtype must not matter (bit-exact: same kernels, same values).  Batch vs single is "equal" to bf16 noise
+    only: the kernel family a deep, small-plane layer runs on depends on the batch size, and the families round at different points
+    (BatchNorm folded into the conv epilogue = one bf16 rounding, conv + apply sweep = two), which through ~36 layers gives 1.3e-2
+    rms / 2e-2 max at EVERY size (64^3, 128^3, 256^3: scripts/debug_batch_indep.py; the fp32 path reads 3.5e-6).  An indexing error
+    would be O(1) over a large part of the volume."""
+    case = {"channels": [32, 64, 128, 256, 512], "shape": [256, 256, 256], "batch": 2, "seed": 71}
+    m = build(case, torch.bfloat16).eval()
+    m.set_training(False)
+    mri, tau, roi, covars, dicts = batch(case)
+    cov32 = covars.to(torch.float32)
+    mixed = torch.stack([cov32[0].to(torch.float64), covars[1]])           # what default_collate makes of a float32 + a float64 sample
+    gen = criterion(cu).gen_loss
+    gen.batch_reduction = None
+    probes = ["model.0.conv.0.conv.weight", "model.1.merge.conv.weight", "model.1.submodule.0.conv.0.conv.weight",
+              "model.1.upconv.up.conv.weight", "deep_modulator_3c.blocks.0.conv.weight", "general_dynamic_prompt"]
+    params = dict(m.named_parameters())
+
+    def run(sl, cov):
+        m.zero_grad(set_to_none=True)
+        pred = m(mri[sl], cov[sl], roi_pred_dicts=dicts[sl], sample_roi_mask=roi[sl])
+        gen(pred, tau[sl], roi[sl]).sum().backward()
+        return pred.detach(), {k: params[k].grad.detach().clone() for k in probes}
+
+    with torch.no_grad():
+        p32 = m(mri, cov32, roi_pred_dicts=dicts, sample_roi_mask=roi)
+        p64 = m(mri, mixed, roi_pred_dicts=dicts, sample_roi_mask=roi)
+    assert torch.equal(p32, p64)
+    pb, gb = run(slice(0, 2), mixed)
+    assert torch.isfinite(pb).all() and float(pb.abs().max()) > 0
+    p0, g0 = run(slice(0, 1), mixed)
+    p1, g1 = run(slice(1, 2), mixed)
+    e0, e1 = check.scaled_err(pb[0:1].cpu().numpy(), p0.cpu().numpy()), check.scaled_err(pb[1:2].cpu().numpy(), p1.cpu().numpy())
+    e2 = check.scaled_err(pb.cpu().numpy(), p64.cpu().numpy())
+    with torch.no_grad():
+        q0 = m(mri[0:1], mixed[0:1], roi_pred_dicts=dicts[0:1], sample_roi_mask=roi[0:1])
+    e3 = check.scaled_err(p64[0:1].cpu().numpy(), q0.cpu().numpy())
+    def rms(a, b):
+        return float((a.float() - b.float()).pow(2).mean().sqrt() / b.float().pow(2).mean().sqrt())
+
+    r0, r1, r3 = rms(pb[0:1], p0), rms(pb[1:2], p1), rms(p64[0:1], q0)
+    print("c5 property errors: batch vs single (autograd path) max", e0, e1, "rms", r0, r1, "| autograd vs no-grad max", e2,
+          "| no-grad batch vs single max", e3, "rms", r3)
+    assert max(e0, e1, e3) < 6e-2 and max(r0, r1, r3) < 2.5e-2, (e0, e1, e3, r0, r1, r3)
+    assert e2 < 5e-2, e2     # autograd path vs fused no-grad path (different bf16 roundings)
+    for k in probes:      # gradients: direction and scale (bf16 gradient noise at this depth is ~1e-1 rms, see the 128^3 train-step test)
+        want, got = (g0[k] + g1[k]).double().flatten(), gb[k].double().flatten()
+        assert torch.isfinite(got).all()
+        cos = float((want * got).sum() / (want.norm() * got.norm() + 1e-300))
+        ratio = float(got.norm() / (want.norm() + 1e-300))
+        assert cos > 0.9 and 0.8 < ratio < 1.25, (k, cos, ratio)
+
+
 @pytest.mark.parametrize("where", ["host", "device"])
 def test_unselected_prompt_keeps_no_gradient(where):
     """A prompt no sample of the batch selects keeps ``grad = None`` (the reference only touches the prompt its ``.item()`` branch
