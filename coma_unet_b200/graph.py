@@ -107,22 +107,38 @@ class GraphedTrainStep:
         dev = next(model.parameters()).device
         return torch.optim.AdamW(model.parameters(), lr=torch.tensor(float(lr), device=dev), fused=True, capturable=True)
 
-    # -- the step itself (eager warm-up and capture run the same code) ------------------------------------------------
-    def _step(self, key):
-        m, inp = self.model, self.inputs
+    # -- the step itself (eager warm-up, capture and ragged batches run the same code) ---------------------------------
+    def _step(self, key, src=None):
+        m = self.model
+        mri, tau, roi, covars, lut = src if src is not None else (self.inputs.mri, self.inputs.tau, self.inputs.roi,
+                                                                  self.inputs.covars, self.inputs.lut)
         self.optimizer.zero_grad(set_to_none=True)
         m._prompt_use_override = key
         try:
-            pred, projected, final_repr = m(inp.mri, inp.covars, roi_pred_dicts=inp.lut, sample_roi_mask=inp.roi)[:3]
+            pred, projected, final_repr = m(mri, covars, roi_pred_dicts=lut, sample_roi_mask=roi)[:3]
         finally:
             m._prompt_use_override = None
-        feats, labels = self.engine.gather_rnc(projected[-1], inp.covars[:, -1])      # [B, 6] labels (:842-845)
+        cov_dev = covars.to(device=pred.device, dtype=torch.float32)
+        feats, labels = self.engine.gather_rnc(projected[-1], cov_dev[:, -1])      # [B, 6] labels (:842-845)
         zeros = torch.zeros(final_repr.size(), device=pred.device)
-        loss, gen, _, _ = self.criterion(pred, inp.tau, inp.roi, (final_repr, zeros, zeros), (feats, labels))
+        loss, gen, _, _ = self.criterion(pred, tau, roi, (final_repr, zeros, zeros), (feats, labels))
         loss.backward()
         self.engine.finish()
         self.optimizer.step()
         return loss.detach(), gen.detach()
+
+    def eager(self, mri, tau, roi, covars, roi_pred_dicts):
+        """One step WITHOUT replay, for a batch whose shape the graphs were not captured for (a ragged last batch).  It runs on the
+        runner's stream: autograd binds every parameter's gradient accumulator to the stream it was first used on, and a capture
+        that meets accumulators bound to another stream fails."""
+        key = self._global_key(covars)
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._step(key, (mri, tau, roi, covars, roi_pred_dicts))
+        cur.wait_stream(self.stream)
+        self.gen_loss = out[1]
+        return out[0]
 
     def _global_key(self, covars) -> Tuple[bool, bool]:
         pos, neg = _host_flags(covars)

@@ -91,8 +91,9 @@ def train_dp(model, criterion, train_loader, validation_loader, epochs, lr, save
         for batch in train_loader:
             mri, tau, roi, _, covars, paths = _unpack(batch)
             mri, tau, roi = mri.to(device, non_blocking=True), tau.to(device, non_blocking=True), roi.to(device, non_blocking=True)
-            if graphed is not None and graphed.matches(mri):
-                loss = graphed(mri, tau, roi, covars, roi_pred_fn(paths))
+            if graphed is not None:      # replay; a ragged last batch runs the same step eagerly on the runner's stream
+                step_fn = graphed if graphed.matches(mri) else graphed.eager
+                loss = step_fn(mri, tau, roi, covars, roi_pred_fn(paths))
                 loss_sum += loss
                 gen_sum += graphed.gen_loss.sum()
                 num_samples += mri.shape[0]

@@ -286,8 +286,10 @@ def test_other_return_conventions_and_attention_dump(tmp_path):
         assert x.shape == mri.shape and len(e) == 5 and len(d) == 4
 
 
-def test_train_loop_checkpoints_and_resumes(tmp_path):
-    """SURVEY 8(f) rank 1+2: the step loop, its checkpoint dict, and resuming from it."""
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_train_loop_checkpoints_and_resumes(tmp_path, cuda_graph):
+    """SURVEY 8(f) rank 1+2: the step loop, its checkpoint dict, and resuming from it -- eagerly and with the step replayed from a
+    CUDA graph (3 samples, batch 2: the ragged last batch of every epoch runs eagerly between replays)."""
     from torch.utils.data import DataLoader
     from coma_unet_b200.train import train_dp
     torch.manual_seed(0)
@@ -303,19 +305,22 @@ def test_train_loop_checkpoints_and_resumes(tmp_path):
         return common.fill_deterministic(m, 3).to(DEV)
 
     m = make()
-    hist = train_dp(m, criterion(cu), loader, loader, epochs=2, lr=1e-3, save_path=str(tmp_path), cuda_id=0, roi_pred_fn=roi_pred_fn)
-    assert len(hist["epoch_avg_loss"]) == 2 and all(torch.isfinite(torch.tensor(hist["epoch_avg_loss"])))
-    assert hist["epoch_avg_loss"][1] < hist["epoch_avg_loss"][0]
+    epochs = 4 if cuda_graph else 2          # two eager warm-up steps come before the first replay
+    hist = train_dp(m, criterion(cu), loader, loader, epochs=epochs, lr=1e-3, save_path=str(tmp_path), cuda_id=0, roi_pred_fn=roi_pred_fn,
+                    cuda_graph=cuda_graph)
+    assert len(hist["epoch_avg_loss"]) == epochs and all(torch.isfinite(torch.tensor(hist["epoch_avg_loss"])))
+    assert hist["epoch_avg_loss"][-1] < hist["epoch_avg_loss"][0]
+    assert (tmp_path / "checkpoints" / "checkpoint_epoch_0.pth").exists()          # numbered copy when epoch % 5 == 0 (:954-955)
     ckpt = torch.load(tmp_path / "checkpoints" / "checkpoint_latest_epoch.pth", map_location="cpu")
-    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "scheduler_state_dict"} and ckpt["epoch"] == 1
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "scheduler_state_dict"} and ckpt["epoch"] == epochs - 1
     # resume (validation.py:221-281 -> train_dp(from_checkpoint=True, optimizer=, scheduler=, start_epoch=))
     m2 = make()
     m2.load_state_dict(ckpt["model_state_dict"])
     opt = torch.optim.AdamW(m2.parameters(), 1e-3)
     opt.load_state_dict(ckpt["optimizer_state_dict"])
-    hist2 = train_dp(m2, criterion(cu), loader, None, epochs=3, lr=1e-3, save_path=str(tmp_path), cuda_id=0, from_checkpoint=True,
+    hist2 = train_dp(m2, criterion(cu), loader, None, epochs=epochs + 1, lr=1e-3, save_path=str(tmp_path), cuda_id=0, from_checkpoint=True,
                      optimizer=opt, scheduler=None, start_epoch=ckpt["epoch"] + 1, roi_pred_fn=roi_pred_fn)
-    assert len(hist2["epoch_avg_loss"]) == 1 and hist2["epoch_avg_loss"][0] < hist["epoch_avg_loss"][1] * 1.2
+    assert len(hist2["epoch_avg_loss"]) == 1 and hist2["epoch_avg_loss"][0] < hist["epoch_avg_loss"][-1] * 1.2
 
 
 def test_graphed_train_step_matches_eager_steps():
