@@ -518,8 +518,11 @@ __global__ void __launch_bounds__(kPwgThreads) conv_pwm_kernel(coma_conv_args a,
 
 static bool pwm_applicable(const coma_conv_args& a) {
   static const bool off = [] { const char* e = getenv("COMA_DISABLE_PWM"); return e && e[0] == '1'; }();
-  return !off && a.dtype == COMA_BF16 && a.ksize == 1 && a.stride == 1 && !a.transposed && (a.Cin == 16 || a.Cin == 32) &&
-         (a.Cout == 16 || a.Cout == 32) && a.y_cn == a.Cout && !a.scale && !a.in_scale && a.act == COMA_ACT_NONE &&
+  // 16 / 32 channels: the top-level gate convs (W_g, W_x: 32 -> 16) and their data gradients; 64 <-> 32: the same at the second level
+  // (on the 128-voxel-tile tcgen05 kernel these streamed at 30-46 "TFLOP/s", i.e. a fifth of the HBM rate)
+  const bool small = (a.Cin == 16 || a.Cin == 32) && (a.Cout == 16 || a.Cout == 32);
+  const bool level2 = (a.Cin == 64 && a.Cout == 32) || (a.Cin == 32 && a.Cout == 64);
+  return !off && a.dtype == COMA_BF16 && a.ksize == 1 && a.stride == 1 && !a.transposed && (small || level2) && a.y_cn == a.Cout && !a.scale && !a.in_scale && a.act == COMA_ACT_NONE &&
          a.x_cs % 2 == 0 && a.x_co % 2 == 0 && a.y_cs % 2 == 0 && a.y_co % 2 == 0 && a.w_bstride % 2 == 0 &&
          reinterpret_cast<uintptr_t>(a.x) % 4 == 0 && reinterpret_cast<uintptr_t>(a.y) % 4 == 0 && reinterpret_cast<uintptr_t>(a.w) % 4 == 0;
 }
@@ -530,6 +533,8 @@ static int launch_pwm(const coma_conv_args& a, cudaStream_t stream) {
   if (a.Cin == 16 && a.Cout == 16) conv_pwm_kernel<16, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
   else if (a.Cin == 32 && a.Cout == 16) conv_pwm_kernel<32, 16><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
   else if (a.Cin == 16 && a.Cout == 32) conv_pwm_kernel<16, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 64 && a.Cout == 32) conv_pwm_kernel<64, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
+  else if (a.Cin == 32 && a.Cout == 64) conv_pwm_kernel<32, 64><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
   else conv_pwm_kernel<32, 32><<<grid, kPwgThreads, 0, stream>>>(a, chunks);
   COMA_CHECK_LAUNCH("conv_pwm");
   return COMA_OK;

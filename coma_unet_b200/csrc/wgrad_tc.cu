@@ -262,8 +262,10 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
   const int cg0 = (pair / cx_slabs) * CHG, cx0 = (pair % cx_slabs) * CHX;
   const int row = threadIdx.x >> 5, e = blockIdx.x * 32 + (threadIdx.x & 31);
   float s = 0.f;
-  if (e < per)
-    for (int c = row; c < gx; c += 8) s += ws[((int64_t)c * pairs + pair) * per + e];
+  if (e < per) {
+#pragma unroll 4
+    for (int c = row; c < gx; c += 8) s += __ldg(ws + ((int64_t)c * pairs + pair) * per + e);
+  }
   part[row][threadIdx.x & 31] = s;
   __syncthreads();
   if (row == 0 && e < per) {

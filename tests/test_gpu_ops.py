@@ -55,6 +55,8 @@ CONV_CASES = [
     (2, 16, 1, 8, 8, 8, 1, 1, False),       # psi / head convs
     (1, 16, 16, 9, 10, 12, 1, 1, False),    # few-channel pointwise streaming kernel, ragged last chunk
     (2, 32, 32, 16, 16, 16, 1, 1, False),   # two statistics chunks per sample
+    (2, 64, 32, 9, 10, 12, 1, 1, False),    # second-level gate convs (64 -> 32) and their data gradient (32 -> 64) on the streaming kernel
+    (1, 32, 64, 16, 16, 16, 1, 1, False),
     (1, 3, 5, 5, 6, 7, 3, 1, False),        # odd channel counts (scalar path)
     (2, 16, 1, 9, 10, 12, 3, 1, False),     # modulator head 16 -> 1: single-pass one-channel weight gradient
     (1, 32, 1, 8, 8, 8, 3, 1, False),
