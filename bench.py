@@ -152,11 +152,14 @@ def make_batch(batch, seed, shape, device=None, pin=False, mixed=False):
     return mri, tau, roi, covars, dicts
 
 
-def build_model(device, shape, dtype=torch.bfloat16, seed=0):
+COMPUTE = {"bf16": (torch.bfloat16, False, "bf16"), "fp32": (torch.float32, False, "f32"), "fp32_tc": (torch.float32, True, "f32 storage, bf16 hi/lo split operands on tcgen05")}
+
+
+def build_model(device, shape, dtype=torch.bfloat16, seed=0, fp32_tc=False):
     import coma_unet_b200 as cu
     torch.manual_seed(seed)
     m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, CHANNELS, [2] * 5, latent_spaces=[2048] * 5, conditional=True,
-                                       decoder_ds=False, compute_dtype=dtype, prompt_shape=tuple(shape))
+                                       decoder_ds=False, compute_dtype=dtype, prompt_shape=tuple(shape), fp32_tensor_cores=fp32_tc)
     with torch.no_grad():   # random-init weights; make the zero-initialised FiLM layers non-trivial
         for name, p in m.named_parameters():
             if ".film.2." in name:
@@ -426,7 +429,8 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
         batch = batch_override or default_batch
         global_batch = batch * world
     torch.cuda.reset_peak_memory_stats(device)
-    model = build_model(device, shape)
+    cdtype, fp32_tc, dtype_label = COMPUTE[args.compute]
+    model = build_model(device, shape, dtype=cdtype, fp32_tc=fp32_tc)
     nb = max(batch, 1)
     mri, tau, roi, covars, dicts = make_batch(nb, 1234 + rank, shape, device=device, mixed=(name == "c5"))
     h_mri, h_tau, h_roi, h_cov, _ = make_batch(nb, 1234 + rank, shape, pin=True, mixed=(name == "c5"))
@@ -576,7 +580,7 @@ def run_workload(name, args, rank, world, local, device, peaks, batch_override=0
     rec = {
         "metric": "volumes_per_sec_" + kind, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": steps,
         "steps_requested": args.steps, "warmup": warm, "ms_per_step": ms / steps, "timed_window_s": ms / 1000.0,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_label, "data": "synthetic",
         "config": {"workload": text % (global_batch if name == "c4" else batch), "config": name, "shape": list(shape),
                    "channels": CHANNELS, "per_gpu_batch": batch if name != "c4" else (global_batch + world - 1) // world,
                    "global_batch": global_batch, "parallelism": f"dp{world}", "active_gpus": n_active,
@@ -637,6 +641,8 @@ def main():
     ap.add_argument("--config", default="", choices=["", "c2", "c3", "c4", "c5"], help="time one named BASELINE config instead")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (c4: the GLOBAL batch split over the ranks)")
     ap.add_argument("--min-seconds", type=float, default=3.0, help="minimum length of the timed window")
+    ap.add_argument("--compute", default="bf16", choices=list(COMPUTE), help="bf16 (the benchmarked path), fp32 (exact, CUDA-core convs), "
+                    "fp32_tc (fp32 storage, 3x3x3 convs on tcgen05 through split-precision operands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default="")

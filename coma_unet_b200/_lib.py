@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcoma_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, BF16_F32OUT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_LEAKY_RELU = 0, 1, 2, 3, 4
 NORM_NONE, NORM_INSTANCE, NORM_BATCH, NORM_GIVEN = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2

@@ -40,7 +40,8 @@ static int check_conv(const coma_conv_args* a, const char* who) {
   COMA_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "%s: kernel size %d not on the hot path (1 or 3)", who, a->ksize);
   COMA_CHECK_ARG(a->stride == 1 || a->stride == 2, "%s: stride %d not on the hot path (1 or 2)", who, a->stride);
   COMA_CHECK_ARG(a->pad == (a->ksize - 1) / 2, "%s: padding must be (k-1)/2", who);
-  COMA_CHECK_ARG(a->dtype == COMA_F32 || a->dtype == COMA_BF16, "%s: bad dtype", who);
+  COMA_CHECK_ARG(a->dtype == COMA_F32 || a->dtype == COMA_BF16 || a->dtype == COMA_BF16_F32OUT, "%s: bad dtype", who);
+  COMA_CHECK_ARG(a->dtype != COMA_BF16_F32OUT || (!a->in_scale && a->w_bstride == 0), "%s: the bf16-in / fp32-out mode takes no prologue and no per-sample weights", who);
   COMA_CHECK_ARG((a->scale == nullptr) == (a->shift == nullptr), "%s: scale and shift go together", who);
   COMA_CHECK_ARG(a->y_cn > 0 && a->y_cn <= a->Cout && a->y_co + a->y_cn <= a->y_cs, "%s: bad output channel view", who);
   COMA_CHECK_ARG(a->x_co + a->Cin <= a->x_cs, "%s: bad input channel view", who);
@@ -64,6 +65,7 @@ static bool tc_enabled() {
   return on;
 }
 static int pick_impl(const coma_conv_args& a) {
+  if (a.dtype == COMA_BF16_F32OUT) return COMA_IMPL_TCGEN05;   // only the per-tap tcgen05 kernel stores fp32 (run_conv rejects what it cannot take)
   if (a.impl != COMA_IMPL_AUTO) return a.impl;
   if (conv_simt_preferred(a)) return COMA_IMPL_SIMT;        // few-channel pointwise: HBM streaming kernel
   return (tc_enabled() && conv_tc_supported(a)) ? COMA_IMPL_TCGEN05 : COMA_IMPL_SIMT;

@@ -49,6 +49,7 @@ struct TcParams {
   float* stats;
   int act, stat_chunks;
   uint32_t tmem_cols;
+  int out_f32;              // COMA_BF16_F32OUT: y is a float tensor (y, y_cs, y_cn in float elements)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -234,6 +235,37 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&raw)[16], const flo
 
 __device__ __forceinline__ float act_neg(int act, float slope) { return act == COMA_ACT_NONE ? 1.f : (act == COMA_ACT_RELU ? 0.f : slope); }
 
+// fp32-store variant of epi_chunk16 (COMA_BF16_F32OUT, per-tap kernel only): same arithmetic, the result is not rounded to bf16
+__device__ __forceinline__ void epi_chunk16_f32(const uint32_t (&raw)[16], const float* cA, const float* cS, const float* cB, bool valid,
+                                                float neg, bool clamp0, float slope, bool stats, float* s1, float* s2,
+                                                float* yrow, int c_abs, int y_cn, bool unit) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float r = __uint_as_float(raw[j]);
+    v[j] = unit ? r + cS[j] : fmaf(cA[j], r, cS[j]);
+    if (stats && valid) {
+      const float t = unit ? v[j] : r + cB[j];
+      s1[j] += t;
+      s2[j] = fmaf(t, t, s2[j]);
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float lo = fminf(v[j], 0.f), hi = fmaxf(v[j], 0.f);
+    v[j] = hi + (clamp0 ? fmaxf(slope * lo, 0.f) : neg * lo);
+  }
+  if (c_abs + 16 <= y_cn && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) reinterpret_cast<float4*>(yrow)[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c_abs + j < y_cn) yrow[j] = v[j];
+  }
+}
+
 // taps of a tile: ordinary conv -> all k^3 taps; transposed conv -> the taps that hit output parity class `cls`
 struct Tap { int dd, dh, dw, widx; };
 __device__ __forceinline__ int num_taps(const TcParams& p, int cls) {
@@ -405,7 +437,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         od = 2 * id + ((tc.cls >> 2) & 1); oh = 2 * ih + ((tc.cls >> 1) & 1); ow = 2 * iw + (tc.cls & 1);
       }
       const int n0 = tc.n_tile * p.NT;
-      __nv_bfloat16* yrow = p.y + ((((int64_t)tc.b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.y_cs + n0;
+      const int64_t yoff = ((((int64_t)tc.b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.y_cs + n0;
+      __nv_bfloat16* yrow = p.y + yoff;
+      float* yrow_f = reinterpret_cast<float*>(p.y) + yoff;
       epi_stage_coef(p.bias, p.scale, p.shift, (int64_t)tc.b * p.Cout, n0, p.NT, cA, cS, (int)threadIdx.x - 64);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -415,7 +449,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float s1c[16], s2c[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1c[j] = 0.f; s2c[j] = 0.f; }
-        epi_chunk16(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs, p.scale == nullptr);
+        if (p.out_f32) epi_chunk16_f32(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow_f + c0, n0 + c0, p.y_cn, p.scale == nullptr);
+        else epi_chunk16(raw, cA + c0, cS + c0, cS + p.NT + c0, valid, neg, clamp0, slope, do_stats, s1c, s2c, yrow + c0, n0 + c0, p.y_cn, p.y_cs, p.scale == nullptr);
         if (do_stats) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -1950,7 +1985,7 @@ bool make_map(CUtensorMap* out, void* base, int rank, const cuuint64_t* dims, co
   return true;
 }
 
-int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin == 32 ? 32 : (cin == 16 ? 16 : 0)); }
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }   // channels per K chunk (= swizzle span / 2)
 int pick_nt(int cout) {
   if (cout <= 256) return cout;
   for (int nt = 256; nt >= 16; nt -= 16)
@@ -2278,7 +2313,8 @@ bool conv_tc_prologue_supported(const coma_conv_args& a) {
 bool conv_tc_supported(const coma_conv_args& a) {
   if (a.in_scale && !conv_tc_prologue_supported(a)) return false;
   if (plan_taps(a).ok) return true;
-  if (a.dtype != COMA_BF16 || a.w_bstride != 0 || a.bias_bstride != 0) return false;
+  if ((a.dtype != COMA_BF16 && a.dtype != COMA_BF16_F32OUT) || a.w_bstride != 0 || a.bias_bstride != 0) return false;
+  if (a.dtype == COMA_BF16_F32OUT && a.in_scale) return false;
   if (a.act == COMA_ACT_SIGMOID) return false;   // epilogue: relu-family activations only
   if (pick_kc(a.Cin) == 0 || a.Cout % 16 != 0 || pick_nt(a.Cout) == 0) return false;
   if (a.x_cs % 8 != 0 || a.x_co % 8 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15)) return false;
@@ -2301,7 +2337,8 @@ int conv_tc_stat_chunks(const coma_conv_args& a) {
     const TapsPlan t = plan_taps(a);
     if (t.ok) return t.cols_w * t.cols_h * t.segs_d * kTapEpi;
   }
-  const HaloPlan h = plan_halo(a);
+  HaloPlan h = plan_halo(a);
+  if (a.dtype != COMA_BF16) h.ok = false;          // fp32-out mode: per-tap kernel only
   if (h.ok) {
     static const bool v3 = [] { const char* e = getenv("COMA_DISABLE_HALO3"); return !(e && e[0] == '1'); }();
     const bool dual = (a.transposed || v3 || h.KCH > 1) && h.NT <= 32 && (h.ctas == 1 || a.transposed || h.s2);   // two epilogue warpgroups -> two partials per segment
@@ -2346,17 +2383,19 @@ static int conv_halo_launch(const coma_conv_args& a, const HaloPlan& h, cudaStre
 }
 
 int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
-  {
-    const PairPlan pp = plan_pair(a);
-    if (pp.ok) return conv_pair_launch(a, pp, stream);
-  }
-  {
-    const TapsPlan t = plan_taps(a);
-    if (t.ok) return conv_taps_launch(a, t, stream);
-  }
-  {
-    const HaloPlan h = plan_halo(a);
-    if (h.ok) return conv_halo_launch(a, h, stream);
+  if (a.dtype == COMA_BF16) {      // the plane-ring / CTA-pair / tap-packed kernels store bf16 only
+    {
+      const PairPlan pp = plan_pair(a);
+      if (pp.ok) return conv_pair_launch(a, pp, stream);
+    }
+    {
+      const TapsPlan t = plan_taps(a);
+      if (t.ok) return conv_taps_launch(a, t, stream);
+    }
+    {
+      const HaloPlan h = plan_halo(a);
+      if (h.ok) return conv_halo_launch(a, h, stream);
+    }
   }
   TcParams p{};
   p.B = a.B; p.Di = a.Di; p.Hi = a.Hi; p.Wi = a.Wi; p.Do = a.Do; p.Ho = a.Ho; p.Wo = a.Wo; p.Cin = a.Cin; p.Cout = a.Cout;
@@ -2369,7 +2408,9 @@ int conv_tc_launch(const coma_conv_args& a, cudaStream_t stream) {
   p.a_bytes = 128u * p.KC * 2u;
   p.b_bytes = (uint32_t)p.NT * p.KC * 2u;
   p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
-  p.y = static_cast<__nv_bfloat16*>(a.y) + a.y_co; p.y_cs = a.y_cs; p.y_cn = a.y_cn;
+  p.out_f32 = a.dtype == COMA_BF16_F32OUT;
+  p.y = p.out_f32 ? reinterpret_cast<__nv_bfloat16*>(static_cast<float*>(a.y) + a.y_co) : static_cast<__nv_bfloat16*>(a.y) + a.y_co;
+  p.y_cs = a.y_cs; p.y_cn = a.y_cn;
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.slope = a.slope; p.stats = a.stats; p.act = a.act;
   p.stat_chunks = p.tiles_w * p.tiles_h * p.tiles_d * p.classes;
   uint32_t cols = 32;

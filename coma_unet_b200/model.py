@@ -259,6 +259,8 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         # storage / compute dtype of the 1..16-channel modulator tail (deep_modulator_3c, fusion_layer, final_pred_head and the
         # one-channel tensors between them); None = compute_dtype
         self.tail_dtype = kwargs.get("tail_dtype", None)
+        # compute_dtype=float32 only: run the 3x3x3 convolutions on the tensor cores at fp32-level accuracy (ops.fp32_split)
+        self.fp32_split = bool(kwargs.get("fp32_tensor_cores", False))
 
         self.projection_heads = nn.ModuleList([
             ProjectionHead(channels[i], int((128 / 2 ** i) ** 3), latent_spaces[i]) for i in range(len(channels))])
@@ -354,6 +356,10 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         return self.final_pred_head(pair, final_relu=True)                             # conv1x1 + IN + PReLU, then ReLU
 
     def forward(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
+        with ops.fp32_split(self.fp32_split and self.compute_dtype == torch.float32):
+            return self._forward(x, covariate, roi_pred_dicts, sample_roi_mask)
+
+    def _forward(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
         if getattr(self, "_coma_stale_caches", False) and getattr(self, "_prompt_use_override", None) is None:
             # eager call after CUDA-graph replays of the training step (coma_unet_b200.graph): the replays updated the parameters
             # without bumping the version counters the packed-weight / folded-BatchNorm caches are keyed on

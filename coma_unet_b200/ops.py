@@ -10,6 +10,7 @@ outputs, BatchNorm folding) is done with torch ops.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import ctypes as C
@@ -195,11 +196,88 @@ def materialized(x):
     return x.materialize() if isinstance(x, Deferred) else x
 
 
+# ------------------------------------------------------------------------------------------------
+# fp32 tensors on the tensor cores: split-precision 3x3x3 convolutions
+# ------------------------------------------------------------------------------------------------
+# With ``compute_dtype=torch.float32`` activations and packed weights are fp32 and the convolutions run on CUDA cores (exact).
+# ``fp32_split(True)`` (model kwarg ``fp32_tensor_cores=True``) moves the 3x3x3 convolutions -- 97 % of the FLOPs -- onto tcgen05 at
+# fp32-level accuracy: x = x_hi + x_lo, w = w_hi + w_lo with bf16 halves (2^-17 relative residual per operand),
+#     conv(x, w) ~= conv([x_hi | x_lo | x_hi], [w_hi | w_hi | w_lo])          (the lo x lo term, 2^-18, is dropped)
+# i.e. ONE bf16 convolution over three times the input channels whose fp32 accumulator is stored unrounded
+# (dtype COMA_BF16_F32OUT, include/coma_b200.h); weight gradients likewise on [g_hi | g_lo] x [x_hi | x_lo] (three of the four
+# blocks of the result are summed).  Everything else of the fp32 path is unchanged.
+FP32_SPLIT = False
+
+
+@contextlib.contextmanager
+def fp32_split(on: bool = True):
+    global FP32_SPLIT
+    prev, FP32_SPLIT = FP32_SPLIT, bool(on)
+    try:
+        yield
+    finally:
+        FP32_SPLIT = prev
+
+
+def _hi_lo(t: torch.Tensor):
+    hi = t.to(torch.bfloat16)
+    return hi, (t - hi.float()).to(torch.bfloat16)
+
+
+def _cat_padded(parts, width):
+    """Channel-concatenate bf16 tensors, each zero-padded to ``width`` channels."""
+    n = parts[0].shape[-1]
+    if n == width:
+        return torch.cat(parts, dim=-1)
+    out = parts[0].new_zeros(*parts[0].shape[:-1], width * len(parts))
+    for i, p in enumerate(parts):
+        out[..., i * width:i * width + n] = p
+    return out
+
+
+def _conv_raw_split(x, wp, bias, *, ksize, stride, transposed, cout_store, scale, shift, slope, act, want_stats, out, kind, alg):
+    B, Di, Hi, Wi, Cin = x.shape
+    taps, cout_comp, _ = wp.shape
+    cin_p, cout_p = _round_up(Cin, 16), _round_up(cout_comp, 16)
+    xh, xl = _hi_lo(x)
+    xs = _cat_padded([xh, xl, xh], cin_p)
+    wh, wl = _hi_lo(wp)
+    ws = torch.zeros(taps, cout_p, 3 * cin_p, device=x.device, dtype=torch.bfloat16)
+    ws[:, :cout_comp, :Cin], ws[:, :cout_comp, cin_p:cin_p + Cin], ws[:, :cout_comp, 2 * cin_p:2 * cin_p + Cin] = wh, wh, wl
+    cout_store = cout_store or cout_comp
+    Do, Ho, Wo = (_out_extent(n, ksize, stride, transposed) for n in (Di, Hi, Wi))
+    y = out if out is not None else torch.empty(B, Do, Ho, Wo, cout_store, device=x.device, dtype=torch.float32)
+
+    def padded(t, fill):
+        if t is None or t.shape[-1] == cout_p:
+            return None if t is None else t.float().contiguous()
+        q = torch.full((*t.shape[:-1], cout_p), fill, device=x.device, dtype=torch.float32)
+        q[..., :t.shape[-1]] = t
+        return q
+
+    a = _conv_args(xs, ws, padded(bias, 0.0), y, ksize=ksize, stride=stride, transposed=transposed, cout_comp=cout_p,
+                   scale=padded(scale, 1.0), shift=padded(shift, 0.0), slope=slope, act=act, alg=alg or (Cin, cout_comp))
+    a.dtype = L.BF16_F32OUT
+    stats = None
+    if want_stats:
+        chunks = L.lib().coma_conv3d_stat_chunks(C.byref(a))
+        stats = torch.empty(B, chunks, cout_p, 2, device=x.device, dtype=torch.float32)
+        a.stats = L.ptr(stats)
+    _run_conv(a, kind or ("coma_convT3d_fprop" if transposed else "coma_conv3d_fprop"))
+    if stats is not None and cout_p != cout_comp:
+        stats = stats[:, :, :cout_comp, :].contiguous()
+    return y, stats
+
+
 def conv_raw(x, wp, bias, *, ksize, stride=1, transposed=False, cout_store=None, scale=None, shift=None, slope=None,
              act=L.ACT_NONE, want_stats=False, out=None, impl=L.IMPL_AUTO, w_bstride=0, bias_bstride=0, kind=None, alg=None):
     """One conv kernel launch on packed weights.  Returns (y, stats_partial or None).  ``x`` may be a Deferred."""
     pro = x if isinstance(x, Deferred) else None
     x = as_vol(pro.raw if pro is not None else x)
+    if (FP32_SPLIT and x.dtype == torch.float32 and pro is None and ksize == 3 and not w_bstride and not bias_bstride
+            and impl == L.IMPL_AUTO and act != L.ACT_SIGMOID):
+        return _conv_raw_split(x, wp, bias, ksize=ksize, stride=stride, transposed=transposed, cout_store=cout_store, scale=scale,
+                               shift=shift, slope=slope, act=act, want_stats=want_stats, out=out, kind=kind, alg=alg)
     B, Di, Hi, Wi, Cin = x.shape
     per = wp.shape[-3:] if w_bstride else wp.shape
     taps, cout_comp, cin_w = per
@@ -241,6 +319,12 @@ def wgrad_raw(g, x, *, ksize, stride, kind="coma_conv3d_wgrad", alg=None):
     g, x = as_vol(g), as_vol(x)
     B, Dg, Hg, Wg, Cg = g.shape
     _, Dx, Hx, Wx, Cx = x.shape
+    if FP32_SPLIT and g.dtype == torch.float32 and ksize == 3:
+        # split-precision weight gradient: [g_hi | g_lo] x [x_hi | x_lo] in bf16, the hi*hi + lo*hi + hi*lo blocks summed in fp32
+        cgp, cxp = _round_up(Cg, 16), _round_up(Cx, 16)
+        g2, x2 = _cat_padded(list(_hi_lo(g)), cgp), _cat_padded(list(_hi_lo(x)), cxp)
+        d2 = wgrad_raw(g2, x2, ksize=ksize, stride=stride, kind=kind, alg=alg or (Cg, Cx))
+        return (d2[:, :Cg, :Cx] + d2[:, cgp:cgp + Cg, :Cx] + d2[:, :Cg, cxp:cxp + Cx]).contiguous()
     if (Cg == 1 and ksize == 3 and stride == 1 and g.dtype == torch.bfloat16 and Cx % 16 == 0 and not _CG1_SIMT
             and not (Cx == 16 and Wg % 32 == 0 and Hg % 8 == 0 and not _CG1_PAD)       # the gathered-A mma.sync kernel takes these
             and ((Wg % 32 == 0 and Hg % 8 == 0) or (Wg == 16 and Hg % 16 == 0)) and Dg >= 4):
@@ -312,6 +396,7 @@ class ConvFn(torch.autograd.Function):
                             cout_store=cout_store, want_stats=cfg.want_stats, impl=cfg.impl, alg=(cin_w, cout_w))
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cout_comp, ctx.has_bias = cfg, cout_comp, bias is not None
+        ctx.split = FP32_SPLIT
         if stats is None:
             stats = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(stats)
@@ -319,6 +404,11 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        with fp32_split(ctx.split):
+            return ConvFn._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy):
         x, weight = ctx.saved_tensors
         cfg: ConvCfg = ctx.cfg
         dy = as_vol(dy if dy.dtype == x.dtype else dy.to(x.dtype))

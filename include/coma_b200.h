@@ -31,7 +31,11 @@ extern "C" {
 typedef struct CUstream_st* coma_stream_t;
 
 enum { COMA_OK = 0, COMA_ERR_INVALID = 1, COMA_ERR_CUDA = 2, COMA_ERR_UNSUPPORTED = 3, COMA_ERR_WORKSPACE = 4 };
-enum { COMA_F32 = 0, COMA_BF16 = 1 };
+enum { COMA_F32 = 0, COMA_BF16 = 1,
+       /* conv fprop / dgrad only: x and w bf16, y stored in fp32 (the accumulator is not rounded).  The split-precision path of the
+        * Python host (ops.conv_raw with fp32 tensors, `fp32_tensor_cores=True`): x = x_hi + x_lo and w = w_hi + w_lo in bf16,
+        * conv(x, w) ~= conv([x_hi | x_lo | x_hi], [w_hi | w_hi | w_lo]) -- fp32-level accuracy (2^-17 per operand) on tcgen05 */
+       COMA_BF16_F32OUT = 2 };
 enum { COMA_ACT_NONE = 0, COMA_ACT_RELU = 1, COMA_ACT_LEAKY = 2 /* PReLU(1 param) and LeakyReLU */, COMA_ACT_SIGMOID = 3,
        COMA_ACT_LEAKY_RELU = 4 /* ReLU(PReLU(u)): final_pred_head + final_act, attn_unet_data_parallel.py:654-656 */ };
 enum { COMA_NORM_NONE = 0, COMA_NORM_INSTANCE = 1, COMA_NORM_BATCH = 2, COMA_NORM_GIVEN = 3 /* eval BN: running stats */ };

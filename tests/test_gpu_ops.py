@@ -130,6 +130,41 @@ def test_conv_fwd_bwd(case, dtype):
     assert err(bp.grad, br.grad) < TOL[dtype]
 
 
+SPLIT_CASES = [(2, 16, 32, 8, 8, 8, 3, 1, False), (1, 32, 32, 9, 7, 10, 3, 1, False), (2, 1, 16, 8, 8, 8, 3, 1, False),
+               (2, 32, 64, 8, 8, 8, 3, 2, False), (2, 64, 32, 4, 4, 4, 3, 2, True), (1, 3, 5, 5, 6, 7, 3, 1, False),
+               (2, 16, 1, 9, 10, 12, 3, 1, False), (1, 64, 128, 16, 16, 16, 3, 1, False), (2, 32, 32, 16, 16, 32, 3, 1, False)]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_fp32_conv_on_tensor_cores_split_precision(case):
+    """ops.fp32_split: fp32 tensors, 3x3x3 convolutions on tcgen05 through bf16 hi/lo operands and an fp32-stored accumulator
+    (dtype COMA_BF16_F32OUT).  Forward, data gradient, weight gradient, bias gradient and the fused statistics hold the fp32
+    tolerance 1e-4 against cuDNN fp32 on arbitrary (not bf16-representable) inputs."""
+    B, Cin, Cout, D, H, W, k, s, tr = case
+    x = rnd(B, Cin, D, H, W, seed=1)
+    wshape = (Cin, Cout, k, k, k) if tr else (Cout, Cin, k, k, k)
+    w = rnd(*wshape, seed=2, scale=(Cin * k ** 3) ** -0.5)
+    b = rnd(Cout, seed=3, scale=0.1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, wr, br, stride=s, padding=1, output_padding=s - 1) if tr else F.conv3d(xr, wr, br, stride=s, padding=1)
+    gy = rnd(*ref.shape, seed=4)
+    ref.backward(gy)
+    xv = to_vol(x, torch.float32).requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    l0 = L.launches
+    with ops.fp32_split(True):
+        y, stats = ops.conv3d(xv, wp, bp, ops.ConvCfg(ksize=k, stride=s, transposed=tr, want_stats=True))
+    assert y.dtype == torch.float32 and err(to_ncdhw(y), ref) < 1e-4
+    tot = stats.sum(dim=1)[:, :Cout]
+    assert err(tot[..., 0], ref.detach().sum(dim=(2, 3, 4))) < 5e-4
+    assert err(tot[..., 1], (ref.detach() ** 2).sum(dim=(2, 3, 4))) < 5e-4
+    y.backward(to_vol(gy, torch.float32))           # the switch travels with the autograd node
+    assert L.launches - l0 >= 3
+    assert err(to_ncdhw(xv.grad), xr.grad) < 1e-4
+    assert err(wp.grad, wr.grad) < 1e-4
+    assert err(bp.grad, br.grad) < 1e-4
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_epilogue_and_channel_sliced_io(dtype):
     B, Cin, Cout, D = 2, 32, 32, 8
