@@ -1,3 +1,5 @@
+"""Eval-mode forward of a batch of two against the same samples run alone, fp32 and bf16, 64^3 .. 256^3, with the first layers whose
+outputs differ: bf16 results depend on the batch size at the level of bf16 rounding noise."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

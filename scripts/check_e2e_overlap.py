@@ -1,3 +1,5 @@
+"""End-to-end inference step time with / without the H2D prefetcher and the D2H sink, eager and graph replay: found that a small
+H2D copy in front of a replay queues behind the next batch's volume upload on the copy engine (hence coma_upload_small)."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,5 @@
+"""Two training steps with the single-tensor, foreach and fused AdamW implementations: losses and weights must agree (they did not
+while the packed-weight cache was keyed by the version counter alone: fused optimizers do not bump it)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,6 @@
+"""One optimizer step replayed from a CUDA graph against the same step run eagerly, for several optimizers (none, SGD, AdamW
+foreach / fused): loss, first conv output and every weight after the step must agree.  This is how the stale packed-weight cache
+behind fused optimizers was found (DESIGN.md section 6, round-2 findings)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -603,7 +603,7 @@ def test_c5_256_crops_mixed_covariate_batch_equals_single_samples():
     alone, and the covariate dtype must not matter (bit-exact: same kernels, same values).  Batch vs single is "equal" to bf16 noise
     only: the kernel family a deep, small-plane layer runs on depends on the batch size, and the families round at different points
     (BatchNorm folded into the conv epilogue = one bf16 rounding, conv + apply sweep = two), which through ~36 layers gives 1.3e-2
-    rms / 2e-2 max at EVERY size (64^3, 128^3, 256^3: scripts/debug_batch_indep.py; the fp32 path reads 3.5e-6).  An indexing error
+    rms / 2e-2 max at EVERY size (64^3, 128^3, 256^3: scripts/check_batch_independence.py; the fp32 path reads 3.5e-6).  An indexing error
     would be O(1) over a large part of the volume."""
     case = {"channels": [32, 64, 128, 256, 512], "shape": [256, 256, 256], "batch": 2, "seed": 71}
     m = build(case, torch.bfloat16).eval()
