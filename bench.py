@@ -132,7 +132,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "window": window}
 
 
-def make_batch(batch, seed, shape, device=None, pin=False, mixed=False):
+def make_batch(batch, seed, shape=(128, 128, 128), device=None, pin=False, mixed=False):
     """(mri, tau, roi, covars, roi dicts) with the VolumeDataset tuple layout; ``mixed``: odd samples are ADNI-shaped (float32
     covariates, VolumeDataset.py:427), even ones A4/combined-shaped (float64, VolumeDataset_ADNI_A4_combined.py:86) -- stacking
     promotes the batch to float64, which is what the default collate hands the model."""
@@ -155,7 +155,7 @@ def make_batch(batch, seed, shape, device=None, pin=False, mixed=False):
 COMPUTE = {"bf16": (torch.bfloat16, False, "bf16"), "fp32": (torch.float32, False, "f32"), "fp32_tc": (torch.float32, True, "f32 storage, bf16 hi/lo split operands on tcgen05")}
 
 
-def build_model(device, shape, dtype=torch.bfloat16, seed=0, fp32_tc=False):
+def build_model(device, shape=(128, 128, 128), dtype=torch.bfloat16, seed=0, fp32_tc=False):
     import coma_unet_b200 as cu
     torch.manual_seed(seed)
     m = cu.ContrastiveAttentionUNET_DP(3, 1, 1, CHANNELS, [2] * 5, latent_spaces=[2048] * 5, conditional=True,
