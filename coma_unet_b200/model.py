@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Sequence
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -243,6 +245,17 @@ class StackedFusionConvLayers(nn.Module):
         return x
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for the work that overlaps the backbone in inference."""
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
     PAD = 16   # channel padding of the small modulator tensors
 
@@ -261,6 +274,8 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         self.tail_dtype = kwargs.get("tail_dtype", None)
         # compute_dtype=float32 only: run the 3x3x3 convolutions on the tensor cores at fp32-level accuracy (ops.fp32_split)
         self.fp32_split = bool(kwargs.get("fp32_tensor_cores", False))
+        # inference only: run the backbone-independent branch of the modulator on a second stream (_forward)
+        self.side_stream = os.environ.get("COMA_SIDE_STREAM", "0") == "1"
 
         self.projection_heads = nn.ModuleList([
             ProjectionHead(channels[i], int((128 / 2 ** i) ** 3), latent_spaces[i]) for i in range(len(channels))])
@@ -322,11 +337,17 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
             t = t.pin_memory().to(device, non_blocking=True)
         return t
 
-    def forward_modulator_with_uq(self, x, out, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
-        """x: user input [B,1,D,H,W] fp32; out: backbone output NDHWC [B,D,H,W,1].  Returns NDHWC [B,D,H,W,1]."""
-        if self.tail_dtype is not None and out.dtype != self.tail_dtype:
-            out = out.to(self.tail_dtype)
-        dev, dt = out.device, out.dtype
+    def _tail_dtype(self):
+        return self.tail_dtype if self.tail_dtype is not None else self.compute_dtype
+
+    def _slim(self, x, dt):
+        return (getattr(self, "slim_inputs", False) and not torch.is_grad_enabled() and dt == torch.bfloat16
+                and x.shape[3] >= 16 and x.shape[4] >= 8)
+
+    def prompt_modulation(self, x, covariate=None, roi_pred_dicts=None, sample_roi_mask=None):
+        """The branch of the modulator that does not depend on the backbone: paint [prompt | saliency | suvr] and run
+        deep_modulator_3c over it (reference :633-646).  x: user input [B,1,D,H,W] fp32.  Returns m1, NDHWC [B,D,H,W,1]."""
+        dev, dt = x.device, self._tail_dtype()
         B = x.shape[0]
         lut = self._roi_lut(roi_pred_dicts, dev)
         cov0 = covariate.reshape(B, -1)[:, 0]
@@ -346,10 +367,18 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
                 used = (bool(flags.any()), bool((~flags).any()))
         # channel padding of the two small inputs: 16 for the per-tap tensor-core path; without autograd the tap-packed
         # kernel takes them as 4 (3 + one zero) and 2 channels
-        slim = getattr(self, "slim_inputs", False) and not torch.is_grad_enabled() and dt == torch.bfloat16 and ops.taps_conv_ok(out)
         painted = ops.RoiPaintFn.apply(self.pos_dynamic_prompt, self.neg_dynamic_prompt, sample_roi_mask, x, lut,
-                                       self._roi_ids, is_pos, 4 if slim else self.PAD, dt, used)
-        m1 = self.deep_modulator_3c(painted)                                           # [B,D,H,W,1]
+                                       self._roi_ids, is_pos, 4 if self._slim(x, dt) else self.PAD, dt, used)
+        return self.deep_modulator_3c(painted)                                         # [B,D,H,W,1]
+
+    def forward_modulator_with_uq(self, x, out, covariate=None, roi_pred_dicts=None, sample_roi_mask=None, m1=None):
+        """x: user input [B,1,D,H,W] fp32; out: backbone output NDHWC [B,D,H,W,1]; m1: prompt_modulation's result when the
+        caller ran it ahead of the backbone.  Returns NDHWC [B,D,H,W,1]."""
+        if self.tail_dtype is not None and out.dtype != self.tail_dtype:
+            out = out.to(self.tail_dtype)
+        if m1 is None:
+            m1 = self.prompt_modulation(x, covariate, roi_pred_dicts, sample_roi_mask)
+        slim = self._slim(x, out.dtype)
         packed = ops.Pack2Fn.apply(m1, self.general_dynamic_prompt, out, 2 if slim else self.PAD)   # [general + m1 | out | 0..]
         fused = self.fusion_layer(packed)                                              # [B,D,H,W,1]
         pair = ops.Pack2Fn.apply(out, None, fused, 2)                                  # [out | fused]
@@ -380,10 +409,22 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
                 landed.record()
                 self._host_flags = (host, landed)
             covariate = covariate.to(device=x.device, dtype=torch.float32, non_blocking=True)
+        m1 = None
+        if self.side_stream and not torch.is_grad_enabled() and x.is_cuda:
+            # inference: the prompt branch of the modulator does not depend on the backbone, so it runs on a second stream
+            # and fills the SMs the small grids of the deep levels leave idle
+            main = torch.cuda.current_stream()
+            side = _side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                m1 = self.prompt_modulation(x, covariate, roi_pred_dicts, sample_roi_mask)
+                m1.record_stream(main)
         xv = ops.ncdhw_to_vol(x, self.compute_dtype)
         with blocks.bn_updates(2):   # the reference's duplicated backbone pass (:664,666) in closed form
             out, encoder_extractions, _ = self._backbone(xv, covariate, defer=not torch.is_grad_enabled())
-        out = self.forward_modulator_with_uq(x, out, covariate, roi_pred_dicts, sample_roi_mask)
+        if m1 is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        out = self.forward_modulator_with_uq(x, out, covariate, roi_pred_dicts, sample_roi_mask, m1=m1)
         pred = ops.vol_to_ncdhw(out).float()
         if not self.training and not self.embeddings_out:
             return pred
