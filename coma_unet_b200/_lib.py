@@ -50,6 +50,11 @@ class WgradArgs(C.Structure):
                 ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class WeightLayoutArgs(C.Structure):
+    _fields_ = [("param", _vp), ("packed", _vp), ("A", _i32), ("B", _i32), ("T", _i32), ("R_pad", _i32), ("C_pad", _i32),
+                ("swap", _i32), ("flip", _i32), ("dtype", _i32), ("unpack", _i32)]
+
+
 class NormFinalizeArgs(C.Structure):
     _fields_ = [("partial", _vp), ("chunks", _i32), ("B", _i32), ("C", _i32), ("V", _i64), ("mode", _i32),
                 ("given_mean", _vp), ("given_var", _vp), ("eps", _f32), ("g", _vp), ("h", _vp), ("A", _vp), ("S", _vp),
@@ -123,6 +128,7 @@ EXPORTS = {
     "coma_convT3d_dgrad": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "coma_conv3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "coma_convT3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
+    "coma_weight_layout": (C.c_int, [C.POINTER(WeightLayoutArgs), _vp]),
     "coma_norm_stats_chunks": (C.c_int, [_i64]),
     "coma_norm_stats": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "coma_gate_stats": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -94,8 +94,10 @@ class AttentionLayer(blocks.AttentionLayer):
         # one concat buffer written in place by its two producers: [att | fromlower]  (replaces torch.cat, :229) -- with autograd
         # too: ops.JoinFn hands the buffer to the merge conv and splits its gradient into two channel-sliced views
         cat = x.new_empty(*x.shape[:-1], 2 * Cn)
-        fromlower = self.upconv(x_sub, covariate, out=cat[..., Cn:])
-        att = self.attention(g=fromlower, x=x, out=cat[..., :Cn])
+        fromlower = gating = self.upconv(x_sub, covariate, out=cat[..., Cn:])
+        if grad and fromlower.requires_grad:
+            fromlower, gating = ops.ForkFn.apply(fromlower)     # its two gradients (a slice of d cat, the gate's dg): one fused sum
+        att = self.attention(g=gating, x=x, out=cat[..., :Cn])
         if self.save_attn is not None:
             att, coeff = att
             save_attention_coeffs(self.save_attn, coeff)

@@ -106,6 +106,11 @@ def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp:
         return hit[1]
     w = weight.detach()
     k = w.shape[2]
+    if _layout_kernel_ok(w, dtype):
+        p = torch.empty(k ** 3, cout_comp, cin_buf, device=w.device, dtype=dtype)
+        _weight_layout(w, p, swap=transposed)
+        cache[key] = ((weight._version, weight.data_ptr(), weight.device, _EPOCH), p)
+        return p
     if transposed:
         p = w.permute(2, 3, 4, 1, 0)
     else:
@@ -118,6 +123,56 @@ def pack_weight(weight: torch.Tensor, transposed: bool, cin_buf: int, cout_comp:
     p = p.to(dtype).contiguous()
     cache[key] = ((weight._version, weight.data_ptr(), weight.device, _EPOCH), p)
     return p
+
+
+PACK_KERNEL = os.environ.get("COMA_DISABLE_PACK_KERNEL", "0") != "1"
+
+
+def _layout_kernel_ok(w: torch.Tensor, dtype: torch.dtype) -> bool:
+    return (PACK_KERNEL and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 5
+            and w.shape[2] * w.shape[3] * w.shape[4] <= 27 and dtype in (torch.float32, torch.bfloat16))
+
+
+def _weight_layout(param, packed, swap=False, flip=False, unpack=False):
+    """coma_weight_layout: parameter tensor [A][B][k,k,k] fp32 <-> tap-major [T][rows][cols] (one launch)."""
+    a = L.WeightLayoutArgs()
+    a.param, a.packed = L.ptr(param), L.ptr(packed)
+    a.A, a.B, a.T = param.shape[0], param.shape[1], packed.shape[0]
+    a.R_pad, a.C_pad = packed.shape[1], packed.shape[2]
+    a.swap, a.flip, a.dtype, a.unpack = int(swap), int(flip), L.dtype_code(packed.dtype), int(unpack)
+    L.call("coma_weight_layout", C.byref(a), L.stream())
+
+
+def pack_adjoint(weight: torch.Tensor, transposed: bool, stride: int, cin_buf: int, cout_comp: int, cout_store: int,
+                 dtype: torch.dtype) -> torch.Tensor:
+    """The data-gradient operand ``[k^3, cin_buf, cout_store]`` of a conv whose forward operand is ``pack_weight(...)``: channels
+    swapped, taps flipped for a stride-1 convolution (its adjoint is a convolution with the mirrored kernel; the adjoint of a
+    strided conv is a transposed conv over the same taps and vice versa).  Cached like pack_weight."""
+    flip = not transposed and stride == 1
+    if not _layout_kernel_ok(weight, dtype):
+        wp = pack_weight(weight, transposed, cin_buf, cout_comp, dtype)[:, :cout_store, :]
+        return (wp.flip(0) if flip else wp).transpose(1, 2).contiguous()
+    cache = weight.__dict__.setdefault("_coma_packed", {})
+    key = ("adjoint", transposed, stride, cin_buf, cout_store, dtype)
+    stamp = (weight._version, weight.data_ptr(), weight.device, _EPOCH)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    w = weight.detach()
+    p = torch.empty(w.shape[2] ** 3, cin_buf, cout_store, device=w.device, dtype=dtype)
+    _weight_layout(w, p, swap=not transposed, flip=flip)
+    cache[key] = (stamp, p)
+    return p
+
+
+def unpack_weight_gradient(dwp: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """``[k^3, rows, cols]`` as the weight-gradient kernels write it -> the parameter's own layout ``[rows_w, cols_w, k, k, k]``."""
+    A, B, k = like.shape[0], like.shape[1], like.shape[2]
+    if _layout_kernel_ok(like, torch.float32) and dwp.dtype == torch.float32 and dwp.is_contiguous():
+        dw = torch.empty(like.shape, device=dwp.device, dtype=torch.float32)
+        _weight_layout(dw, dwp, unpack=True)
+        return dw
+    return dwp[:, :A, :B].reshape(k, k, k, A, B).permute(3, 4, 0, 1, 2).contiguous()
 
 
 def invalidate_weight_caches(module: torch.nn.Module) -> None:
@@ -417,25 +472,22 @@ class ConvFn(torch.autograd.Function):
         dx = dw = db = None
         cin_w, cout_w = (weight.shape[0], weight.shape[1]) if cfg.transposed else (weight.shape[1], weight.shape[0])
         if ctx.needs_input_grad[0]:
-            wp = pack_weight(weight, cfg.transposed, cin_buf, ctx.cout_comp, x.dtype)[:, :cout_store, :]
+            adj = pack_adjoint(weight, cfg.transposed, cfg.stride, cin_buf, ctx.cout_comp, cout_store, x.dtype)
             alg = (cout_w, cin_w)
             if cfg.transposed:      # adjoint of convT(stride s) = conv(stride s), channels swapped
-                adj = wp.transpose(1, 2).contiguous()
                 dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=False, kind="coma_convT3d_dgrad", alg=alg)
             elif cfg.stride == 1:   # adjoint of conv(stride 1) = conv with flipped taps, channels swapped
-                adj = wp.flip(0).transpose(1, 2).contiguous()
                 dx, _ = conv_raw(dy, adj, None, ksize=k, stride=1, transposed=False, kind="coma_conv3d_dgrad", alg=alg)
             else:                   # adjoint of conv(stride s) = convT(stride s)
-                adj = wp.transpose(1, 2).contiguous()
                 dx, _ = conv_raw(dy, adj, None, ksize=k, stride=cfg.stride, transposed=True, kind="coma_conv3d_dgrad", alg=alg)
             assert dx.shape == x.shape, (dx.shape, x.shape)
         if ctx.needs_input_grad[1]:
             if cfg.transposed:
                 dwp = wgrad_raw(x, dy, ksize=k, stride=cfg.stride, kind="coma_convT3d_wgrad", alg=(cin_w, cout_w))   # [T, cin_buf, cout_store]
-                dw = dwp[:, :cin_w, :cout_w].reshape(k, k, k, cin_w, cout_w).permute(3, 4, 0, 1, 2).contiguous()
+                dw = unpack_weight_gradient(dwp, weight)
             else:
                 dwp = wgrad_raw(dy, x, ksize=k, stride=cfg.stride, alg=(cout_w, cin_w))           # [T, cout_store, cin_buf]
-                dw = dwp[:, :cout_w, :cin_w].reshape(k, k, k, cout_w, cin_w).permute(3, 4, 0, 1, 2).contiguous()
+                dw = unpack_weight_gradient(dwp, weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             if cfg.bias_grad_zero:
                 db = torch.zeros(cout_w, device=x.device, dtype=torch.float32)
@@ -633,6 +685,26 @@ class JoinFn(torch.autograd.Function):
         return (d[..., :Ca] if ctx.needs_input_grad[0] else None), (d[..., Ca:] if ctx.needs_input_grad[1] else None), None
 
 
+class ForkFn(torch.autograd.Function):
+    """t -> (t, t) for a tensor with two consumers one of which hands back a channel-sliced gradient (ops.JoinFn): backward sums the
+    two gradients in ONE strided-aware streaming pass (coma_norm_film_act_fwd with identity coefficients and a residual).
+    Autograd's own accumulation takes the non-vectorised elementwise kernel for a strided operand -- 3 x the HBM time."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return alias(t), alias(t)
+
+    @staticmethod
+    def backward(ctx, da, db):
+        if da is None or db is None:
+            return da if db is None else db
+        da, db = as_vol(da), as_vol(db)
+        if db.dtype != da.dtype:
+            db = db.to(da.dtype)
+        one, zero = _identity_coefficients(da)
+        return affine_act(da, one, zero, None, L.ACT_NONE, residual=db)
+
+
 class Concat2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
@@ -657,12 +729,16 @@ class Concat2Fn(torch.autograd.Function):
 _ident_cache: dict = {}
 
 
-def _copy_channels(src, dst):
-    B, D, H, W, Cn = src.shape
+def _identity_coefficients(src):
+    B, Cn = src.shape[0], src.shape[-1]
     key = (src.device, B, Cn)
     if key not in _ident_cache:
         _ident_cache[key] = (torch.ones(B, Cn, device=src.device), torch.zeros(B, Cn, device=src.device))
-    one, zero = _ident_cache[key]
+    return _ident_cache[key]
+
+
+def _copy_channels(src, dst):
+    one, zero = _identity_coefficients(src)
     return affine_act(src, one, zero, None, L.ACT_NONE, out=dst)
 
 

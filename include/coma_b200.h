@@ -324,6 +324,27 @@ int coma_prepare_volumes(const coma_prepare_args* a, coma_stream_t stream);
  * ------------------------------------------------------------------------------------------- */
 int coma_upload_small(float* dst, const float* host_values, int64_t n, coma_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight layout transforms between the reference's parameter layout and the tap-major layout every conv entry point above
+ * takes.  `param` is the framework's tensor [A][B][T] fp32 with the T = k^3 taps fastest: nn.Conv3d.weight [Cout][Cin][k][k][k]
+ * (monai Convolution, attn_unet_data_parallel.py:166-205) or nn.ConvTranspose3d.weight [Cin][Cout][k][k][k] (:207-222).
+ * `packed` is [T][R_pad][C_pad] in `dtype`, (r, c) = (a, b) or, with `swap`, (b, a); rows / columns beyond A / B are zero.
+ *   forward operand     Conv3d: swap 0            ConvTranspose3d: swap 1           (rows = Cout, cols = Cin)
+ *   data-gradient one   Conv3d stride 1: swap 1, flip 1   stride 2: swap 1   ConvTranspose3d: swap 0   (rows = Cin, cols = Cout)
+ * `unpack` = 1 goes the other way for a weight gradient: packed fp32 [T][R_pad][C_pad] (coma_conv3d_wgrad's dw) -> param.
+ * One launch each; replaces the permute / pad / cast / flip chain of framework kernels (~350 launches per training step).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* param;        /* [A][B][T] fp32: read when packing, written when unpacking */
+  void* packed;       /* [T][R_pad][C_pad] */
+  int A, B, T;        /* T <= 27 */
+  int R_pad, C_pad;
+  int swap, flip;     /* flip: tap t <-> T - 1 - t (the adjoint of a stride-1 convolution) */
+  int dtype;          /* of `packed`: COMA_BF16 or COMA_F32 */
+  int unpack;
+} coma_weight_layout_args;
+int coma_weight_layout(const coma_weight_layout_args* a, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -727,3 +727,30 @@ def test_prepare_volumes_full_size_properties():
     assert torch.equal(m2, m) and torch.equal(r2, r)
     with pytest.raises(RuntimeError):
         prepare_volumes(mri.cpu(), None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# coma_weight_layout: one launch instead of the permute / pad / cast / flip chain (bit-exact: it only moves and rounds)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cout,cin,k,transposed,stride", [
+    (16, 1, 3, False, 1), (32, 16, 3, False, 1), (64, 32, 3, False, 2), (32, 64, 3, True, 2), (1, 16, 1, False, 1),
+    (16, 32, 1, False, 1), (256, 128, 3, False, 1), (20, 7, 3, False, 1), (7, 20, 3, True, 2), (1, 16, 3, False, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_weight_layout_kernel_matches_the_tensor_op_chain(monkeypatch, cout, cin, k, transposed, stride, dtype):
+    shape = (cin, cout, k, k, k) if transposed else (cout, cin, k, k, k)
+    w = torch.nn.Parameter(rnd(*shape, seed=cout * 131 + cin))
+    cin_buf, cout_comp = -(-cin // 16) * 16, -(-cout // 16) * 16
+    cout_store = cout_comp if cout > 4 else cout          # narrow outputs are stored unpadded (the dy of the data gradient)
+    got_fwd = ops.pack_weight(w, transposed, cin_buf, cout_comp, dtype)
+    got_adj = ops.pack_adjoint(w, transposed, stride, cin_buf, cout_comp, cout_store, dtype)
+    rows, cols = (cin_buf, cout_store) if transposed else (cout_store, cin_buf)
+    dwp = rnd(k ** 3, rows, cols, seed=5)
+    got_dw = ops.unpack_weight_gradient(dwp, w)
+    monkeypatch.setattr(ops, "PACK_KERNEL", False)
+    w.__dict__.pop("_coma_packed", None)
+    want_fwd = ops.pack_weight(w, transposed, cin_buf, cout_comp, dtype)
+    want_adj = ops.pack_adjoint(w, transposed, stride, cin_buf, cout_comp, cout_store, dtype)
+    want_dw = ops.unpack_weight_gradient(dwp, w)
+    for got, want in ((got_fwd, want_fwd), (got_adj, want_adj), (got_dw, want_dw)):
+        assert got.shape == want.shape and got.dtype == want.dtype and got.is_contiguous()
+        assert torch.equal(got, want)
