@@ -325,59 +325,78 @@ __global__ void __launch_bounds__(kThreads) affine_act_small_kernel(coma_affine_
 
 // ---- backward finalize: partial sums -> dg, dh, dslope and dx = P*dz + Q + R*x coefficients -------
 __global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(coma_affine_act_bwd_args a, int chunks) {
-  // one block per channel c; threads stride over (b, chunk)
-  __shared__ float sh[kThreads / 32];
-  __shared__ float tot[3];
+  // one block per channel c.  The (b, chunk) partials of FB batch entries are summed at a time -- 3 * FB independent reductions
+  // behind ONE barrier pair (this kernel sits between the two sweeps of every norm backward: its latency is on the step's
+  // critical path 39 times per training step) -- then thread b turns the sums of batch entry b into its coefficients.
+  constexpr int FB = 4, NW = kThreads / 32;
+  __shared__ float sh[NW][FB * 3];
+  __shared__ float red[3];                 // batch mode: sum_b g*dh, sum_b g*dg; always: sum_b dslope terms
   const int c = blockIdx.x, B = a.B, C = a.C;
-  float m1 = 0.f, m2 = 0.f, ds = 0.f;
-  for (int b = 0; b < B; ++b) {
-    float s[3] = {0.f, 0.f, 0.f};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m1 = 0.f, m2 = 0.f, ds = 0.f;      // meaningful in thread 0
+  for (int b0 = 0; b0 < B; b0 += FB) {
+    float s[FB][3];
+#pragma unroll
+    for (int j = 0; j < FB; ++j) s[j][0] = s[j][1] = s[j][2] = 0.f;
     for (int ch = threadIdx.x; ch < chunks; ch += kThreads) {
-      const float* p = a.partial + (((int64_t)b * chunks + ch) * C + c) * 3;
-      s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        if (b0 + j < B) {
+          const float* p = a.partial + (((int64_t)(b0 + j) * chunks + ch) * C + c) * 3;
+          s[j][0] += p[0]; s[j][1] += p[1]; s[j][2] += p[2];
+        }
+      }
     }
-    for (int q = 0; q < 3; ++q) {
-      float v = warp_sum(s[q]);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
-        tot[q] = t;
+#pragma unroll
+    for (int j = 0; j < FB; ++j) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float v = warp_sum(s[j][q]);
+        if (lane == 0) sh[warp][j * 3 + q] = v;
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const int i = b * C + c;
-      const float g = a.g ? a.g[i] : 1.f;
-      a.dh[i] = tot[0];
-      a.dg[i] = tot[1];
-      m1 += g * tot[0];
-      m2 += g * tot[1];
-      ds += tot[2];
+    if (threadIdx.x < FB * 3) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += sh[w][threadIdx.x];
+      sh[0][threadIdx.x] = t;              // only thread x reads / writes column x of row 0 here
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < FB && b0 + j < B; ++j) {
+        const int i = (b0 + j) * C + c;
+        const float g = a.g ? a.g[i] : 1.f;
+        a.dh[i] = sh[0][j * 3 + 0];
+        a.dg[i] = sh[0][j * 3 + 1];
+        m1 += g * sh[0][j * 3 + 0];
+        m2 += g * sh[0][j * 3 + 1];
+        ds += sh[0][j * 3 + 2];
+      }
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) {
     if (a.dslope && (a.act == COMA_ACT_LEAKY || a.act == COMA_ACT_LEAKY_RELU)) atomicAdd(a.dslope, ds);
-    const float invBV = 1.f / ((float)B * (float)a.V), invV = 1.f / (float)a.V;
-    for (int b = 0; b < B; ++b) {
-      const int i = b * C + c;
-      const float g = a.g ? a.g[i] : 1.f;
-      const float P = a.A[i], rstd = a.rstd[i], mean = a.mean[i];
-      float R = 0.f, Q = 0.f;
-      if (a.mode == COMA_NORM_INSTANCE) {
-        R = -P * rstd * a.dg[i] * invV;
-        Q = -P * a.dh[i] * invV - R * mean;
-      } else if (a.mode == COMA_NORM_BATCH) {
-        R = -rstd * rstd * m2 * invBV;
-        Q = -rstd * m1 * invBV - R * mean;
-      }
-      (void)g;
-      a.coef[i * 3 + 0] = P;
-      a.coef[i * 3 + 1] = Q;
-      a.coef[i * 3 + 2] = R;
+    red[0] = m1; red[1] = m2;
+  }
+  __syncthreads();
+  m1 = red[0]; m2 = red[1];
+  const float invBV = 1.f / ((float)B * (float)a.V), invV = 1.f / (float)a.V;
+  for (int b = threadIdx.x; b < B; b += kThreads) {
+    const int i = b * C + c;
+    const float P = a.A[i], rstd = a.rstd[i], mean = a.mean[i];
+    float R = 0.f, Q = 0.f;
+    if (a.mode == COMA_NORM_INSTANCE) {
+      R = -P * rstd * a.dg[i] * invV;      // dg / dh of entry b were written by thread 0 of this block before the barrier above
+      Q = -P * a.dh[i] * invV - R * mean;
+    } else if (a.mode == COMA_NORM_BATCH) {
+      R = -rstd * rstd * m2 * invBV;
+      Q = -rstd * m1 * invBV - R * mean;
     }
+    a.coef[i * 3 + 0] = P;
+    a.coef[i * 3 + 1] = Q;
+    a.coef[i * 3 + 2] = R;
   }
 }
 

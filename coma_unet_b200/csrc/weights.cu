@@ -4,8 +4,8 @@
 // replaces the permute / zero-fill / slice-assign / cast / flip / transpose chain of ATen kernels (~7 launches per conv and
 // training step, ~350 per step of the north-star model).
 //
-// A block moves a 16 x 16 tile of (a, b) pairs with all their taps through shared memory, so that both the parameter side
-// (runs of 16 * T consecutive floats) and the packed side (runs of 16 consecutive channels per tap) are accessed in full sectors.
+// A block moves a 16 x 16 tile of (a, b) pairs with a group of taps (9 of 27) through shared memory, so that both the parameter
+// side (runs of consecutive taps) and the packed side (runs of 16 consecutive channels per tap) are accessed in whole sectors.
 #include "common.cuh"
 
 namespace coma {
@@ -13,50 +13,82 @@ namespace coma {
 constexpr int WT = 16;
 constexpr int WT_MAX_TAPS = 27;
 
-template <typename PT>
+// TZ taps per block (blockIdx.z selects the group; TZ = 0: all T taps, run-time trip counts).  With a compile-time TZ both loops
+// unroll completely, so a block has all its loads in flight at once: these kernels run ~125 times per training step on a few KB
+// each and their LATENCY is what the step pays (8 us per launch with the rolled loops, see profiles/r02_ncu_launch_list_train_b4).
+template <typename PT, int TZ>
 __global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restrict__ param, PT* __restrict__ packed, int A, int B,
                                                           int T, int R_pad, int C_pad, int swap, int flip) {
-  __shared__ float tile[WT * WT * WT_MAX_TAPS];
+  __shared__ float tile[WT * WT * (TZ ? TZ : WT_MAX_TAPS)];
+  const int tz = TZ ? TZ : T;
   const int r0 = blockIdx.y * WT, c0 = blockIdx.x * WT;
   const int a0 = swap ? c0 : r0, b0 = swap ? r0 : c0;
-  const int n = WT * WT * T;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const int ai = i / (WT * T), rem = i - ai * (WT * T);
-    const int bi = rem / T, t = rem - bi * T;
+  const int t0 = blockIdx.z * tz;                                  // packed taps [t0, t0 + tz)
+  const int s0 = flip ? T - t0 - tz : t0;                          // the source taps they come from (mirrored: same set, reversed)
+  constexpr int ITER = TZ ? TZ : WT_MAX_TAPS;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (!TZ && i >= WT * WT * tz) break;
+    const int ai = i / (WT * tz), rem = i - ai * (WT * tz);
+    const int bi = rem / tz, tt = rem - bi * tz;
     const int a = a0 + ai, b = b0 + bi;
-    tile[i] = (a < A && b < B) ? __ldg(param + ((size_t)a * B + b) * T + t) : 0.f;
+    tile[i] = (a < A && b < B) ? __ldg(param + ((size_t)a * B + b) * T + s0 + tt) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * WT * WT; i += 256) {
-    const int t = i / (WT * WT), rc = i - t * (WT * WT);
-    const int ri = rc / WT, ci = rc - ri * WT;
-    const int r = r0 + ri, c = c0 + ci;
-    if (r >= R_pad || c >= C_pad) continue;
-    const int ai = swap ? ci : ri, bi = swap ? ri : ci;
-    const int ts = flip ? T - 1 - t : t;
-    Elem<PT>::st(packed + ((size_t)t * R_pad + r) * C_pad + c, tile[(ai * WT + bi) * T + ts]);
+  const int rc = threadIdx.x, ri = rc / WT, ci = rc - ri * WT;
+  const int r = r0 + ri, c = c0 + ci;
+  if (r >= R_pad || c >= C_pad) return;
+  const int ai = swap ? ci : ri, bi = swap ? ri : ci;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    if (!TZ && k >= tz) break;
+    const int tt = flip ? tz - 1 - k : k;
+    Elem<PT>::st(packed + ((size_t)(t0 + k) * R_pad + r) * C_pad + c, tile[(ai * WT + bi) * tz + tt]);
   }
 }
 
 // packed fp32 [T][R_pad][C_pad] (a weight gradient as the kernels produce it) -> parameter layout [A][B][T], (r, c) = (a, b)
+template <int TZ>
 __global__ void __launch_bounds__(256) weight_unpack_kernel(const float* __restrict__ packed, float* __restrict__ param, int A, int B,
                                                             int T, int R_pad, int C_pad) {
-  __shared__ float tile[WT * WT * WT_MAX_TAPS];
-  const int a0 = blockIdx.y * WT, b0 = blockIdx.x * WT;
-  for (int i = threadIdx.x; i < T * WT * WT; i += 256) {
-    const int t = i / (WT * WT), rc = i - t * (WT * WT);
-    const int ai = rc / WT, bi = rc - ai * WT;
+  __shared__ float tile[WT * WT * (TZ ? TZ : WT_MAX_TAPS)];
+  const int tz = TZ ? TZ : T;
+  const int a0 = blockIdx.y * WT, b0 = blockIdx.x * WT, t0 = blockIdx.z * tz;
+  constexpr int ITER = TZ ? TZ : WT_MAX_TAPS;
+  {
+    const int rc = threadIdx.x, ai = rc / WT, bi = rc - ai * WT;
     const int a = a0 + ai, b = b0 + bi;
-    tile[(ai * WT + bi) * T + t] = (a < A && b < B && a < R_pad && b < C_pad) ? __ldg(packed + ((size_t)t * R_pad + a) * C_pad + b) : 0.f;
+    const bool ok = a < A && b < B && a < R_pad && b < C_pad;
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      if (!TZ && k >= tz) break;
+      tile[(ai * WT + bi) * tz + k] = ok ? __ldg(packed + ((size_t)(t0 + k) * R_pad + a) * C_pad + b) : 0.f;
+    }
   }
   __syncthreads();
-  const int n = WT * WT * T;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const int ai = i / (WT * T), rem = i - ai * (WT * T);
-    const int bi = rem / T, t = rem - bi * T;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (!TZ && i >= WT * WT * tz) break;
+    const int ai = i / (WT * tz), rem = i - ai * (WT * tz);
+    const int bi = rem / tz, tt = rem - bi * tz;
     const int a = a0 + ai, b = b0 + bi;
-    if (a < A && b < B) param[((size_t)a * B + b) * T + t] = tile[i];
+    if (a < A && b < B) param[((size_t)a * B + b) * T + t0 + tt] = tile[i];
   }
+}
+
+template <typename PT>
+static void launch_pack(const coma_weight_layout_args* a, cudaStream_t s) {
+  const float* src = static_cast<const float*>(a->param);
+  PT* dst = static_cast<PT*>(a->packed);
+  const unsigned gx = (a->C_pad + WT - 1) / WT, gy = (a->R_pad + WT - 1) / WT;
+  if (a->T == 27)
+    weight_pack_kernel<PT, 9><<<dim3(gx, gy, 3), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad, a->swap, a->flip);
+  else if (a->T == 1)
+    weight_pack_kernel<PT, 1><<<dim3(gx, gy, 1), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad, a->swap, a->flip);
+  else
+    weight_pack_kernel<PT, 0><<<dim3(gx, gy, 1), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad, a->swap, a->flip);
 }
 
 }  // namespace coma
@@ -69,18 +101,21 @@ extern "C" int coma_weight_layout(const coma_weight_layout_args* a, coma_stream_
   cudaStream_t s = (cudaStream_t)stream;
   if (a->unpack) {
     COMA_CHECK_ARG(a->dtype == COMA_F32 && !a->swap && !a->flip, "coma_weight_layout: unpack takes an fp32 packed tensor, no swap / flip");
-    dim3 grid((a->B + WT - 1) / WT, (a->A + WT - 1) / WT);
-    weight_unpack_kernel<<<grid, 256, 0, s>>>((const float*)a->packed, (float*)a->param, a->A, a->B, a->T, a->R_pad, a->C_pad);
-  } else {
-    dim3 grid((a->C_pad + WT - 1) / WT, (a->R_pad + WT - 1) / WT);
-    if (a->dtype == COMA_BF16)
-      weight_pack_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const float*)a->param, (__nv_bfloat16*)a->packed, a->A, a->B, a->T,
-                                                              a->R_pad, a->C_pad, a->swap, a->flip);
-    else if (a->dtype == COMA_F32)
-      weight_pack_kernel<float><<<grid, 256, 0, s>>>((const float*)a->param, (float*)a->packed, a->A, a->B, a->T, a->R_pad,
-                                                     a->C_pad, a->swap, a->flip);
+    const float* src = static_cast<const float*>(a->packed);
+    float* dst = static_cast<float*>(a->param);
+    const unsigned gx = (a->B + WT - 1) / WT, gy = (a->A + WT - 1) / WT;
+    if (a->T == 27)
+      weight_unpack_kernel<9><<<dim3(gx, gy, 3), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad);
+    else if (a->T == 1)
+      weight_unpack_kernel<1><<<dim3(gx, gy, 1), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad);
     else
-      COMA_CHECK_ARG(false, "coma_weight_layout: dtype must be COMA_BF16 or COMA_F32");
+      weight_unpack_kernel<0><<<dim3(gx, gy, 1), 256, 0, s>>>(src, dst, a->A, a->B, a->T, a->R_pad, a->C_pad);
+  } else if (a->dtype == COMA_BF16) {
+    launch_pack<__nv_bfloat16>(a, s);
+  } else if (a->dtype == COMA_F32) {
+    launch_pack<float>(a, s);
+  } else {
+    COMA_CHECK_ARG(false, "coma_weight_layout: dtype must be COMA_BF16 or COMA_F32");
   }
   COMA_CHECK_LAUNCH("weight_layout");
   return COMA_OK;

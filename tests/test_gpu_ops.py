@@ -734,7 +734,7 @@ def test_prepare_volumes_full_size_properties():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cout,cin,k,transposed,stride", [
     (16, 1, 3, False, 1), (32, 16, 3, False, 1), (64, 32, 3, False, 2), (32, 64, 3, True, 2), (1, 16, 1, False, 1),
-    (16, 32, 1, False, 1), (256, 128, 3, False, 1), (20, 7, 3, False, 1), (7, 20, 3, True, 2), (1, 16, 3, False, 1)])
+    (16, 32, 1, False, 1), (256, 128, 3, False, 1), (20, 7, 3, False, 1), (7, 20, 3, True, 2), (1, 16, 3, False, 1), (24, 40, 2, False, 1)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_weight_layout_kernel_matches_the_tensor_op_chain(monkeypatch, cout, cin, k, transposed, stride, dtype):
     shape = (cin, cout, k, k, k) if transposed else (cout, cin, k, k, k)
