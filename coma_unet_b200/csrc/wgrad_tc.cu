@@ -252,34 +252,57 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
 // Deterministic finish: dw[tap][cg][cx] = sum over the CTAs of a channel pair of their partial blocks, in CTA order (a plain
 // store: dw need not be zeroed).  ws: [gx][pairs][27][CHG][CHX].
+template <int ROWS>
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int gx, int pairs,
                                                            int cx_slabs, int CHG, int CHX, int Cg, int Cx) {
-  // 32 elements per block; the eight 32-thread rows each sum every eighth CTA block, then row 0 adds the eight row sums in row
-  // order: a fixed association for a given grid, whatever order the CTAs finished in
-  __shared__ float part[8][32];
-  const int per = 27 * CHG * CHX;
+  // A block covers 1024 / ROWS consecutive elements as float4 lanes x ROWS rows; row r sums the CTA blocks r, r + ROWS, ...
+  // (16-byte loads, all in flight at once: the kernel is a latency chain over 16 MB at most), then a fixed tree over the rows --
+  // one association for a given grid, whatever order the CTAs finished in.  ROWS follows gx (many channel pairs = few CTAs per
+  // pair: with 8 rows for gx = 1 seven of eight threads idled, 120 us for the 512 -> 256 merge conv).
+  constexpr int LANES = 256 / ROWS;
+  __shared__ float4 part[ROWS][LANES];
+  const int per = 27 * CHG * CHX;                                  // a multiple of 32
   const int pair = blockIdx.y;
   const int cg0 = (pair / cx_slabs) * CHG, cx0 = (pair % cx_slabs) * CHX;
-  const int row = threadIdx.x >> 5, e = blockIdx.x * 32 + (threadIdx.x & 31);
-  float s = 0.f;
+  const int lane = threadIdx.x % LANES, row = threadIdx.x / LANES, e = (blockIdx.x * LANES + lane) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e < per) {
-#pragma unroll 4
-    for (int c = row; c < gx; c += 8) s += __ldg(ws + ((int64_t)c * pairs + pair) * per + e);
+#pragma unroll 8
+    for (int c = row; c < gx; c += ROWS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + ((int64_t)c * pairs + pair) * per + e));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  part[row][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (row == 0 && e < per) {
-    float t = part[0][threadIdx.x];
+  if (ROWS > 1) {
+    part[row][lane] = s;
+    __syncthreads();
 #pragma unroll
-    for (int r = 1; r < 8; ++r) t += part[r][threadIdx.x];
-    const int tap = e / (CHG * CHX), r2 = e % (CHG * CHX);
-    dw[((int64_t)tap * Cg + cg0 + r2 / CHX) * Cx + cx0 + r2 % CHX] = t;
+    for (int st = ROWS / 2; st >= 1; st >>= 1) {
+      if (row < st) {
+        const float4 o = part[row + st][lane];
+        float4& m = part[row][lane];
+        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+      }
+      __syncthreads();
+    }
+    s = part[0][lane];
+  }
+  if (row == 0 && e < per) {
+    const int tap = e / (CHG * CHX), r2 = e % (CHG * CHX);         // the four elements share a tap and a gradient channel
+    float* o = dw + ((int64_t)tap * Cg + cg0 + r2 / CHX) * Cx + cx0 + r2 % CHX;
+    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
   }
 }
 
 static int wgrad_finish(const WgParams& p, const coma_wgrad_args& a, int gx, int pairs, int CHG, int CHX, cudaStream_t stream) {
-  dim3 grid((unsigned)((27 * CHG * CHX + 31) / 32), (unsigned)pairs);
-  wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, p.dw, gx, pairs, p.cx_slabs, CHG, CHX, a.Cg, a.Cx);
+  const int vecs = 27 * CHG * CHX / 4;                             // CHG * CHX is a multiple of 256
+#define COMA_FINISH(ROWS)                                                                                                 \
+  wgrad_finish_kernel<ROWS><<<dim3((unsigned)((vecs + 256 / ROWS - 1) / (256 / ROWS)), (unsigned)pairs), 256, 0, stream>>>( \
+      p.ws, p.dw, gx, pairs, p.cx_slabs, CHG, CHX, a.Cg, a.Cx)
+  if (gx >= 24) COMA_FINISH(32);
+  else if (gx >= 4) COMA_FINISH(4);
+  else COMA_FINISH(1);
+#undef COMA_FINISH
   COMA_CHECK_LAUNCH("wgrad_finish");
   return COMA_OK;
 }
@@ -501,6 +524,7 @@ int launch_wgrad_s2_tc(const coma_wgrad_args& a, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(wgrad_s2_tc_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   dim3 grid((unsigned)gx, (unsigned)pairs);
+  COMA_CHECK_ARG(reinterpret_cast<uintptr_t>(a.workspace) % 16 == 0, "coma_conv3d_wgrad: workspace must be 16-byte aligned");
   p.ws = (a.workspace && a.workspace_bytes >= (int64_t)gx * pairs * 27 * 32 * 32 * 4) ? static_cast<float*>(a.workspace) : nullptr;
   wgrad_s2_tc_kernel<BW><<<grid, kThreads, smem, stream>>>(tmE, tmO, tmG, p);
   COMA_CHECK_LAUNCH("wgrad_s2_tc");
@@ -561,6 +585,7 @@ int launch_wgrad_tc(const coma_wgrad_args& a, cudaStream_t stream) {
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(wgrad_tc_kernel<CHX, CHG, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
   dim3 grid((unsigned)gx, (unsigned)pairs);
+  COMA_CHECK_ARG(reinterpret_cast<uintptr_t>(a.workspace) % 16 == 0, "coma_conv3d_wgrad: workspace must be 16-byte aligned");
   p.ws = (a.workspace && a.workspace_bytes >= (int64_t)gx * pairs * 27 * CHG * CHX * 4) ? static_cast<float*>(a.workspace) : nullptr;
   wgrad_tc_kernel<CHX, CHG, BW><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   COMA_CHECK_LAUNCH("wgrad_tc");

@@ -118,7 +118,7 @@ typedef struct {
   int32_t ksize, stride, pad;
   int32_t dtype;
   int32_t impl;
-  /* Optional (NULL / 0 = off): caller-owned scratch of at least coma_conv3d_wgrad_workspace_size() bytes.  With it the tcgen05
+  /* Optional (NULL / 0 = off): caller-owned, 16-byte aligned scratch of at least coma_conv3d_wgrad_workspace_size() bytes.  With it the tcgen05
    * kernels write one partial [27][Cg][Cx] block per CTA and a second kernel sums the blocks in a fixed order and STORES dw
    * (dw need not be zeroed): bit-identical results from run to run.  Without it the CTAs add into a zeroed dw with fp32 atomics
    * (order-dependent low bits). */

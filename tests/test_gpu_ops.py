@@ -53,6 +53,9 @@ CONV_CASES = [
     (1, 32, 16, 3, 5, 4, 3, 2, True),
     (2, 32, 16, 8, 8, 8, 1, 1, False),
     (2, 16, 1, 8, 8, 8, 1, 1, False),       # psi / head convs
+    (2, 32, 1, 17, 18, 20, 1, 1, False),    # one-output pointwise weight gradient: streaming kernel, several blocks, ragged tail
+    (1, 64, 1, 16, 16, 16, 1, 1, False),
+    (3, 8, 1, 9, 10, 12, 1, 1, False),
     (1, 16, 16, 9, 10, 12, 1, 1, False),    # few-channel pointwise streaming kernel, ragged last chunk
     (2, 32, 32, 16, 16, 16, 1, 1, False),   # two statistics chunks per sample
     (2, 64, 32, 9, 10, 12, 1, 1, False),    # second-level gate convs (64 -> 32) and their data gradient (32 -> 64) on the streaming kernel
@@ -260,6 +263,11 @@ NORM_BULK_CASES = [
     (L.NORM_BATCH, L.ACT_RELU, 512, False, False, (3, 4, 4, 4)),
     (L.NORM_BATCH, L.ACT_SIGMOID, 64, False, True, (1, 9, 10, 12)),
     (L.NORM_INSTANCE, L.ACT_NONE, 128, False, False, (2, 16, 16, 16)),
+    # dense one-channel volumes (gate psi, modulator heads): the 8-voxels-per-load sweeps, and a ragged size that must not take them
+    (L.NORM_INSTANCE, L.ACT_LEAKY_RELU, 1, False, False, (2, 32, 32, 32)),
+    (L.NORM_BATCH, L.ACT_SIGMOID, 1, False, False, (2, 16, 24, 40)),
+    (L.NORM_BATCH, L.ACT_RELU, 1, False, True, (1, 16, 16, 16)),
+    (L.NORM_INSTANCE, L.ACT_LEAKY, 1, False, False, (2, 7, 9, 11)),
 ]
 
 
