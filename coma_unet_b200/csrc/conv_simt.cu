@@ -279,7 +279,21 @@ __global__ void __launch_bounds__(256) conv_pw_from1_kernel(coma_conv_args a) {
   const float slope = a.slope ? __ldg(a.slope) : 0.f;
   const T* xb = static_cast<const T*>(a.x) + (int64_t)b * Vo * a.x_cs + a.x_co;
   T* yb = static_cast<T*>(a.y) + (int64_t)b * Vo * a.y_cs + a.y_co + cvec * 8;
-  for (int64_t v = (int64_t)blockIdx.x * lanes + vlane; v < Vo; v += (int64_t)gridDim.x * lanes) {
+  const int64_t step = (int64_t)gridDim.x * lanes;
+  int64_t v = (int64_t)blockIdx.x * lanes + vlane;
+  for (; v + 3 * step < Vo; v += 4 * step) {          // four voxels in flight per thread: the loads first, then the four stores
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = Elem<T>::ld(xb + (v + u * step) * a.x_cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = act_fwd(a.act, fmaf(xv[u], w8[e], h8[e]), slope);
+      store8(yb + (v + u * step) * a.y_cs, o);
+    }
+  }
+  for (; v < Vo; v += step) {
     const float xv = Elem<T>::ld(xb + v * a.x_cs);
     float o[8];
 #pragma unroll
@@ -768,6 +782,55 @@ __global__ void __launch_bounds__(256) wgrad_cg1_k1_kernel(coma_wgrad_args a, in
   }
 }
 
+// The same for a dense x with 1, 2 or 4 channels (final_pred_head 2 -> 1): a 16-byte load covers 8 / CX voxels.
+template <typename T, int CX>
+__global__ void __launch_bounds__(256) wgrad_cg1_k1_few_kernel(coma_wgrad_args a, int64_t vchunk) {
+  constexpr int VPT = 8 / CX;
+  __shared__ float red[8][CX];
+  const int64_t total = (int64_t)a.B * a.Dg * a.Hg * a.Wg;
+  const int64_t begin = (int64_t)blockIdx.x * vchunk, end = min(begin + vchunk, total);     // vchunk is a multiple of 8
+  const T* gp = static_cast<const T*>(a.g) + a.g_co;
+  const T* xp = static_cast<const T*>(a.x);
+  float acc[CX];
+#pragma unroll
+  for (int c = 0; c < CX; ++c) acc[c] = 0.f;
+  int64_t o = begin + (int64_t)threadIdx.x * VPT;
+  constexpr int64_t STEP = 256 * VPT;
+  for (; o + 3 * STEP + VPT <= end; o += 4 * STEP) {
+    float xv[4][8], gv[4][VPT];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      load8_stream(xp + (o + u * STEP) * CX, xv[u]);
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) gv[u][j] = Elem<T>::ld(gp + (o + u * STEP + j) * a.g_cs);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < VPT; ++j)
+#pragma unroll
+        for (int c = 0; c < CX; ++c) acc[c] = fmaf(gv[u][j], xv[u][j * CX + c], acc[c]);
+  }
+  for (; o < end; o += STEP)
+    for (int j = 0; j < VPT && o + j < end; ++j) {
+      const float gv = Elem<T>::ld(gp + (o + j) * a.g_cs);
+#pragma unroll
+      for (int c = 0; c < CX; ++c) acc[c] = fmaf(gv, Elem<T>::ld(xp + (o + j) * CX + c), acc[c]);
+    }
+#pragma unroll
+  for (int c = 0; c < CX; ++c) {
+    const float v = warp_sum(acc[c]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < CX) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(a.dw + threadIdx.x, t);
+  }
+}
+
 // One-channel gradient (the 16 -> 1 modulator heads), k3 s1: walk the x voxels ONCE per kd plane instead of once per tap.
 // A thread owns one 8-channel vector of an x voxel and accumulates its contribution to the nine (kh,kw) taps of its kd:
 // dw[kd,kh,kw][c] += x[i][c] * g[i - k + 1]; the 72 partial sums are reduced per block and added atomically.
@@ -860,6 +923,24 @@ int wgrad_simt_launch(const coma_wgrad_args& a, cudaStream_t stream) {
     if (a.dtype == COMA_BF16) wgrad_cg1_k1_kernel<__nv_bfloat16><<<nch, 256, 0, stream>>>(a, vchunk);
     else wgrad_cg1_k1_kernel<float><<<nch, 256, 0, stream>>>(a, vchunk);
     COMA_CHECK_LAUNCH("wgrad_cg1_k1");
+    return COMA_OK;
+  }
+  if (a.Cg == 1 && a.ksize == 1 && a.stride == 1 && (a.Cx == 1 || a.Cx == 2 || a.Cx == 4) && a.x_cs == a.Cx && a.x_co == 0 &&
+      (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && a.Dg == a.Dx && a.Hg == a.Hx && a.Wg == a.Wx) {
+    const int64_t want = (int64_t)num_sms() * 8;
+    int64_t vchunk = ((total + want - 1) / want + 7) / 8 * 8;
+    if (vchunk < 4096) vchunk = 4096;
+    const unsigned nch = (unsigned)((total + vchunk - 1) / vchunk);
+#define COMA_CG1_FEW(T)                                                                          \
+    do {                                                                                         \
+      if (a.Cx == 1) wgrad_cg1_k1_few_kernel<T, 1><<<nch, 256, 0, stream>>>(a, vchunk);          \
+      else if (a.Cx == 2) wgrad_cg1_k1_few_kernel<T, 2><<<nch, 256, 0, stream>>>(a, vchunk);     \
+      else wgrad_cg1_k1_few_kernel<T, 4><<<nch, 256, 0, stream>>>(a, vchunk);                    \
+    } while (0)
+    if (a.dtype == COMA_BF16) COMA_CG1_FEW(__nv_bfloat16);
+    else COMA_CG1_FEW(float);
+#undef COMA_CG1_FEW
+    COMA_CHECK_LAUNCH("wgrad_cg1_k1_few");
     return COMA_OK;
   }
   if (a.Cg == 1 && a.Cx <= 64) {

@@ -56,6 +56,9 @@ CONV_CASES = [
     (2, 32, 1, 17, 18, 20, 1, 1, False),    # one-output pointwise weight gradient: streaming kernel, several blocks, ragged tail
     (1, 64, 1, 16, 16, 16, 1, 1, False),
     (3, 8, 1, 9, 10, 12, 1, 1, False),
+    (2, 2, 1, 9, 10, 12, 1, 1, False),      # final_pred_head 2 -> 1: dense few-channel x, 4 voxels per 16-byte load, ragged tail
+    (1, 4, 1, 33, 32, 40, 1, 1, False),     # several blocks, the four-deep main loop
+    (2, 1, 1, 16, 16, 24, 1, 1, False),
     (1, 16, 16, 9, 10, 12, 1, 1, False),    # few-channel pointwise streaming kernel, ragged last chunk
     (2, 32, 32, 16, 16, 16, 1, 1, False),   # two statistics chunks per sample
     (2, 64, 32, 9, 10, 12, 1, 1, False),    # second-level gate convs (64 -> 32) and their data gradient (32 -> 64) on the streaming kernel
