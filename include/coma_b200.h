@@ -345,6 +345,33 @@ typedef struct {
 } coma_weight_layout_args;
 int coma_weight_layout(const coma_weight_layout_args* a, coma_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * All FiLM MLPs of a model in one launch, forward and backward.  Every conditioned layer of the reference owns
+ * film = Linear(n_cov, 64) -> ReLU -> Linear(64, 2 C) on the per-sample covariates (CondConv call sites, attn_unet_data_parallel.py:
+ * 126,285-306,318-325,354-367; specification in DESIGN.md section 4); under autograd these are ~12 framework launches per layer
+ * and step (two GEMMs, ReLU, bias sums, chunk / cat) on [B x 6] .. [B x 512] matrices.  One block per layer here.
+ *   forward : hid_l = relu(cov[:, :n_l] W1_l^T + b1_l)          [B][64]   (kept for backward)
+ *             out_l = hid_l W2_l^T + b2_l, stored as [2][B][C_l]: dgamma block, then beta block
+ *   backward: dW1, db1, dW2, db2 of every layer from d_dgamma_l / d_beta_l ([B][C_l] each, NULL = zero); no covariate gradient.
+ * Parameter layouts are nn.Linear's: W1 [64][n_l], b1 [64], W2 [2 C_l][64], b2 [2 C_l], all fp32.
+ * ------------------------------------------------------------------------------------------- */
+#define COMA_FILM_MAX_LAYERS 32
+#define COMA_FILM_HIDDEN 64
+typedef struct {
+  int32_t n_layers, B, cov_stride;         /* cov: [B][cov_stride] fp32, layer l reads its first n_cov[l] columns */
+  const float* cov;
+  float* hid;                              /* [n_layers][B][64] */
+  int32_t n_cov[COMA_FILM_MAX_LAYERS], C[COMA_FILM_MAX_LAYERS];
+  const float* W1[COMA_FILM_MAX_LAYERS]; const float* b1[COMA_FILM_MAX_LAYERS];
+  const float* W2[COMA_FILM_MAX_LAYERS]; const float* b2[COMA_FILM_MAX_LAYERS];
+  float* out[COMA_FILM_MAX_LAYERS];        /* forward: [2][B][C_l] */
+  const float* d_dgamma[COMA_FILM_MAX_LAYERS]; const float* d_beta[COMA_FILM_MAX_LAYERS];     /* backward inputs */
+  float* dW1[COMA_FILM_MAX_LAYERS]; float* db1[COMA_FILM_MAX_LAYERS];                         /* backward outputs (stored) */
+  float* dW2[COMA_FILM_MAX_LAYERS]; float* db2[COMA_FILM_MAX_LAYERS];
+} coma_film_args;
+int coma_film_mlp_fwd(const coma_film_args* a, coma_stream_t stream);
+int coma_film_mlp_bwd(const coma_film_args* a, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
