@@ -55,6 +55,15 @@ class WeightLayoutArgs(C.Structure):
                 ("swap", _i32), ("flip", _i32), ("dtype", _i32), ("unpack", _i32)]
 
 
+FILM_MAX_LAYERS = 32
+
+
+class FilmArgs(C.Structure):
+    _fields_ = [("n_layers", _i32), ("B", _i32), ("cov_stride", _i32), ("cov", _vp), ("hid", _vp),
+                ("n_cov", _i32 * FILM_MAX_LAYERS), ("C", _i32 * FILM_MAX_LAYERS)] + [
+        (name, _vp * FILM_MAX_LAYERS) for name in ("W1", "b1", "W2", "b2", "out", "d_dgamma", "d_beta", "dW1", "db1", "dW2", "db2")]
+
+
 class NormFinalizeArgs(C.Structure):
     _fields_ = [("partial", _vp), ("chunks", _i32), ("B", _i32), ("C", _i32), ("V", _i64), ("mode", _i32),
                 ("given_mean", _vp), ("given_var", _vp), ("eps", _f32), ("g", _vp), ("h", _vp), ("A", _vp), ("S", _vp),
@@ -129,6 +138,8 @@ EXPORTS = {
     "coma_conv3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "coma_convT3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "coma_weight_layout": (C.c_int, [C.POINTER(WeightLayoutArgs), _vp]),
+    "coma_film_mlp_fwd": (C.c_int, [C.POINTER(FilmArgs), _vp]),
+    "coma_film_mlp_bwd": (C.c_int, [C.POINTER(FilmArgs), _vp]),
     "coma_norm_stats_chunks": (C.c_int, [_i64]),
     "coma_norm_stats": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "coma_gate_stats": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

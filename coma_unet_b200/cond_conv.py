@@ -80,6 +80,21 @@ class FilmBatch:
         FilmBatch.active = {id(m): (out[l, :, :m.out_channels], out[l, :, cmax:cmax + m.out_channels])
                             for l, m in enumerate(self.mods)}
 
+    def compute_train(self, covariate):
+        """Under autograd: the same slices from ONE fused launch each way (ops.FilmAllFn) instead of a Linear -> ReLU -> Linear
+        chain per layer (~185 framework launches per training step of the north-star model).  False = not applicable."""
+        c = covariate.reshape(covariate.shape[0], -1)
+        if not (ops.FUSED_FILM and self.mods and c.is_cuda and c.dtype == torch.float32 and c.shape[0] <= 64
+                and len(self.mods) <= 32 and all(p.dtype == torch.float32 for m in self.mods for p in m.film.parameters())):
+            return False
+        if c.stride(1) != 1:
+            c = c.contiguous()
+        meta = tuple((m.num_covars, m.out_channels) for m in self.mods)
+        params = [p for m in self.mods for p in (m.film[0].weight, m.film[0].bias, m.film[2].weight, m.film[2].bias)]
+        outs = ops.FilmAllFn.apply(c, meta, *params)
+        FilmBatch.active = {id(m): (outs[2 * l], outs[2 * l + 1]) for l, m in enumerate(self.mods)}
+        return True
+
     @staticmethod
     def clear():
         FilmBatch.active = {}
@@ -141,7 +156,7 @@ class CondConvolution(Convolution):
             return y
         film = None
         if self.film is not None and c is not None:
-            film = FilmBatch.active.get(id(self)) if not torch.is_grad_enabled() else None
+            film = FilmBatch.active.get(id(self))      # filled by the model for this forward (no-grad: batched GEMMs, grad: fused MLP kernel)
             if film is None or film[0].shape[0] != c.shape[0]:
                 film = self.film(c).chunk(2, dim=-1)
         return super().forward(x, film=film, out=out, defer=defer)

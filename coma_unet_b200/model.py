@@ -171,14 +171,17 @@ class ObservableAttentionUnet(nn.Module):
         return self
 
     def _film_batch(self, covariate):
-        """No-grad forward: evaluate every FiLM MLP up front in two batched GEMMs (cond_conv.FilmBatch)."""
-        if covariate is None or torch.is_grad_enabled() or not self.conditional:
+        """Evaluate every FiLM MLP up front (cond_conv.FilmBatch): two batched GEMMs without autograd, one fused launch each way
+        (ops.FilmAllFn) with it."""
+        if covariate is None or not self.conditional:
             return False
         fb = getattr(self, "_fb", None)
         if fb is None:
             fb = self._fb = cond_conv.FilmBatch(self)
         if covariate.shape[-1] < max((m.num_covars for m in fb.mods), default=0):
             return False
+        if torch.is_grad_enabled():
+            return fb.compute_train(covariate)
         fb.compute(covariate)
         return True
 
@@ -316,6 +319,14 @@ class ContrastiveAttentionUNET_DP(ObservableAttentionUnet):
         """Parameters whose gradient exists only if the local batch selects them (:638-639): DataParallelEngine reduces them
         after backward, in a fixed order, instead of from their hooks."""
         return [self.pos_dynamic_prompt, self.neg_dynamic_prompt]
+
+    def end_of_backward_parameters(self):
+        """Parameters whose gradients all arrive from ONE autograd node at the very end of backward: the FiLM MLPs, evaluated
+        together ahead of the backbone (ops.FilmAllFn).  Left in the ordinary buckets they would hold every bucket back until
+        then; DataParallelEngine reduces them (< 1 MB) after backward with the data-dependent ones."""
+        if not ops.FUSED_FILM:
+            return []
+        return [p for m in self.modules() if isinstance(m, cond_conv.CondConvolution) and m.film is not None for p in m.film.parameters()]
 
     # -- ROI lookup table: host dicts -> one small pinned upload, no per-ROI device work ---------------
     def roi_lut_host(self, roi_pred_dicts):

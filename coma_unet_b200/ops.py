@@ -685,6 +685,75 @@ class JoinFn(torch.autograd.Function):
         return (d[..., :Ca] if ctx.needs_input_grad[0] else None), (d[..., Ca:] if ctx.needs_input_grad[1] else None), None
 
 
+FUSED_FILM = os.environ.get("COMA_DISABLE_FILM_FUSED", "0") != "1"
+
+
+class FilmAllFn(torch.autograd.Function):
+    """Every FiLM MLP of a model (Linear(n, 64) -> ReLU -> Linear(64, 2C) per conditioned layer, specification: DESIGN.md section 4) in ONE
+    launch forward and ONE backward (coma_film_mlp_fwd / _bwd) instead of ~12 framework launches per layer and training step.
+
+    ``FilmAllFn.apply(cov, meta, W1_0, b1_0, W2_0, b2_0, W1_1, ...)`` with cov ``[B, n]`` fp32 and meta = ((n_cov_l, C_l), ...)
+    returns (dgamma_0, beta_0, dgamma_1, ...), each ``[B, C_l]`` fp32 and contiguous."""
+
+    @staticmethod
+    def _args(cov, meta, params):
+        a = L.FilmArgs()
+        a.n_layers, a.B, a.cov_stride, a.cov = len(meta), cov.shape[0], cov.stride(0), L.ptr(cov)
+        for l, (n, Cn) in enumerate(meta):
+            a.n_cov[l], a.C[l] = n, Cn
+            a.W1[l], a.b1[l], a.W2[l], a.b2[l] = (L.ptr(p) for p in params[4 * l:4 * l + 4])
+        return a
+
+    @staticmethod
+    def forward(ctx, cov, meta, *params):
+        assert cov.dim() == 2 and cov.dtype == torch.float32 and cov.stride(1) == 1 and len(params) == 4 * len(meta)
+        params = [p.detach() if p.is_contiguous() else p.detach().contiguous() for p in params]
+        B = cov.shape[0]
+        flat = torch.empty(sum(2 * B * Cn for _, Cn in meta), device=cov.device, dtype=torch.float32)
+        hid = torch.empty(len(meta), B, 64, device=cov.device, dtype=torch.float32)
+        a = FilmAllFn._args(cov, meta, params)
+        a.hid = L.ptr(hid)
+        outs, off = [], 0
+        for l, (_, Cn) in enumerate(meta):
+            o = flat[off:off + 2 * B * Cn]
+            a.out[l] = L.ptr(o)
+            outs += [alias(o[:B * Cn].view(B, Cn)), alias(o[B * Cn:].view(B, Cn))]
+            off += 2 * B * Cn
+        L.call("coma_film_mlp_fwd", C.byref(a), L.stream())
+        ctx.save_for_backward(cov, hid, *params)
+        ctx.meta = meta
+        ctx.set_materialize_grads(False)       # backward must see None for the outputs nobody consumed
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        cov, hid, *params = ctx.saved_tensors
+        meta = ctx.meta
+        a = FilmAllFn._args(cov, meta, params)
+        a.hid = L.ptr(hid)
+        gflat = torch.empty(sum(p.numel() for p in params), device=cov.device, dtype=torch.float32)
+        pgrads, off, keep = [], 0, []
+        for l in range(len(meta)):
+            for k, name in enumerate(("dW1", "db1", "dW2", "db2")):
+                p = params[4 * l + k]
+                g = alias(gflat[off:off + p.numel()].view(p.shape))
+                getattr(a, name)[l] = L.ptr(g)
+                pgrads.append(g)
+                off += p.numel()
+            for k, name in enumerate(("d_dgamma", "d_beta")):
+                g = grads[2 * l + k]
+                if g is not None:
+                    g = g.float().contiguous()
+                    keep.append(g)
+                getattr(a, name)[l] = L.ptr(g)
+        L.call("coma_film_mlp_bwd", C.byref(a), L.stream())
+        out = []
+        for l in range(len(meta)):
+            used = grads[2 * l] is not None or grads[2 * l + 1] is not None       # a layer the forward never consumed keeps grad None
+            out += [pgrads[4 * l + k] if used and ctx.needs_input_grad[2 + 4 * l + k] else None for k in range(4)]
+        return (None, None, *out)
+
+
 class ForkFn(torch.autograd.Function):
     """t -> (t, t) for a tensor with two consumers one of which hands back a channel-sliced gradient (ops.JoinFn): backward sums the
     two gradients in ONE strided-aware streaming pass (coma_norm_film_act_fwd with identity coefficients and a residual).

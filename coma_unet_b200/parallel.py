@@ -14,7 +14,7 @@ wrap sites commented out at validation.py:268-269) with what it would have meant
   (``pos_dynamic_prompt`` / ``neg_dynamic_prompt`` get a gradient only if a local sample selects them,
   attn_unet_data_parallel.py:638-639), so "launch a bucket when its last hook fires" would pair different buffers
   across ranks.  Parameters are therefore split into *early* ones, whose hook fires on every rank in every step,
-  and *late* ones (declared by the model through ``data_dependent_parameters()``, plus every parameter that fired
+  and *late* ones (declared by the model through ``data_dependent_parameters()`` / ``end_of_backward_parameters()``, plus every parameter that fired
   on no rank in the first step: ``reweigh*``, ``modulator*``, projection heads 0-3).  Early buckets are launched
   by a cursor, bucket b only after buckets 0..b-1; late buckets are launched in ``finish()``, in index order, and
   only if some rank used one of their parameters (a decision taken from the globally reduced mask, hence identical
@@ -78,8 +78,10 @@ class DataParallelEngine:
         self.cap = int(float(os.environ.get("COMA_DP_BUCKET_MB", bucket_mb)) * 1024 * 1024)
         declared = late
         if declared is None:
-            fn = getattr(model, "data_dependent_parameters", None)
-            declared = fn() if callable(fn) else []
+            declared = []
+            for name in ("data_dependent_parameters", "end_of_backward_parameters"):
+                fn = getattr(model, name, None)
+                declared += list(fn()) if callable(fn) else []
         ids = {id(p) for p in declared}
         self.late = torch.tensor([id(p) in ids for p in self.params], dtype=torch.bool)
         self.learned = False         # the never-firing parameters join ``late`` after the first step

@@ -765,3 +765,39 @@ def test_weight_layout_kernel_matches_the_tensor_op_chain(monkeypatch, cout, cin
     for got, want in ((got_fwd, want_fwd), (got_adj, want_adj), (got_dw, want_dw)):
         assert got.shape == want.shape and got.dtype == want.dtype and got.is_contiguous()
         assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# coma_film_mlp_fwd / _bwd: every FiLM MLP of a model in one launch each way, against the per-layer nn.Sequential chain
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 4, 7])
+def test_fused_film_mlps_match_the_per_layer_modules(B):
+    torch.manual_seed(11)
+    layers = [(5, 16), (6, 32), (6, 256), (5, 1), (6, 24)]          # (num_covars, out_channels)
+    mods = [torch.nn.Sequential(torch.nn.Linear(n, 64), torch.nn.ReLU(), torch.nn.Linear(64, 2 * c)).to(DEV) for n, c in layers]
+    cov = rnd(B, 6, seed=3)
+    params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
+    outs = ops.FilmAllFn.apply(cov, tuple(layers), *params)
+    assert len(outs) == 2 * len(layers)
+    gs = [rnd(B, c, seed=20 + l) for l, (_, c) in enumerate(layers)]
+    hs = [rnd(B, c, seed=40 + l) for l, (_, c) in enumerate(layers)]
+    skip = 3                                                         # a layer whose outputs nobody consumes keeps grad None
+    loss = sum((outs[2 * l] * gs[l]).sum() + (outs[2 * l + 1] * hs[l]).sum() for l in range(len(layers)) if l != skip)
+    loss.backward()
+    got = [None if p.grad is None else p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    for l, (m, (n, c)) in enumerate(zip(mods, layers)):
+        dgamma, beta = m(cov[:, :n]).chunk(2, dim=-1)
+        assert outs[2 * l].is_contiguous() and outs[2 * l].shape == (B, c)
+        # fp32 sums in a different order; absolute floor because a one-element tensor (B = 1, C = 1) can sit next to zero
+        close = lambda a, b: torch.allclose(a, b, rtol=1e-4, atol=1e-5)      # noqa: E731
+        assert close(outs[2 * l], dgamma) and close(outs[2 * l + 1], beta), (l, (outs[2 * l] - dgamma).abs().max())
+        if l != skip:
+            ((dgamma * gs[l]).sum() + (beta * hs[l]).sum()).backward()
+    for i, p in enumerate(params):
+        if i // 4 == skip:
+            assert got[i] is None
+        else:
+            assert got[i].shape == p.grad.shape
+            assert torch.allclose(got[i], p.grad, rtol=1e-4, atol=1e-5), (i, (got[i] - p.grad).abs().max(), p.grad.abs().max())
