@@ -145,3 +145,9 @@ def test_roi_table_and_prompt_declarations():
     assert lut[0, 0, 0] == pytest.approx(dicts[0][m.roi_names[0]]["loc"]) and lut[1, 4, 0] == 0.0      # nan_to_num, :641
     dd = m.data_dependent_parameters()
     assert len(dd) == 2 and dd[0] is m.pos_dynamic_prompt and dd[1] is m.neg_dynamic_prompt
+    # the FiLM MLPs (evaluated by one fused launch each way under autograd) are declared to the data-parallel engine as
+    # "gradient arrives at the end of backward": every film parameter, nothing else, none of the data-dependent ones
+    late = m.end_of_backward_parameters()
+    film = [p for name, p in m.named_parameters() if ".film." in name]
+    assert film and {id(p) for p in late} == {id(p) for p in film}
+    assert not {id(p) for p in late} & {id(p) for p in dd}

@@ -29,6 +29,10 @@ class Toy(nn.Module):
     def data_dependent_parameters(self):
         return [self.pos, self.neg]
 
+    def end_of_backward_parameters(self):
+        """Like the fused FiLM MLPs of the real model: parameters the engine should not wait for in the early buckets."""
+        return list(self.head.parameters()) if getattr(self, "declare_head_late", False) else []
+
 
 def make_data(flags=(1, 1, 1, 1)):
     g = torch.Generator().manual_seed(0)
@@ -52,13 +56,17 @@ def single_process(flags=(1, 1, 1, 1)):
     return {k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()}
 
 
-def worker(rank, world, port, out, flags, bucket_mb, declare):
+def worker(rank, world, port, out, flags, bucket_mb, declare, head_late=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(1 + 7 * rank)                                       # replicas differ until the engine broadcasts rank 0's
     m = Toy()
+    m.declare_head_late = head_late
     eng = DataParallelEngine(m, world_size=world, bucket_mb=bucket_mb, late=None if declare else [])
     assert len(eng.buckets) > 2
+    if head_late:                                                         # the declared parameters sit in late buckets only
+        late_ids = {id(p) for b in range(eng.n_early, len(eng.buckets)) for p in (eng.params[i] for i in eng.buckets[b])}
+        assert all(id(p) in late_ids for p in m.head.parameters())
     x, y, labels, flag = make_data(flags)
     sl = slice(rank * 2, rank * 2 + 2)
     logs = []
@@ -76,14 +84,14 @@ def worker(rank, world, port, out, flags, bucket_mb, declare):
     dist.destroy_process_group()
 
 
-def run_two_ranks(flags, bucket_mb=0.0005, declare=True):
+def run_two_ranks(flags, bucket_mb=0.0005, declare=True, head_late=False):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, out, flags, bucket_mb, declare)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, out, flags, bucket_mb, declare, head_late)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict((r, (g, logs, sc)) for r, g, logs, sc in (out.get(), out.get()))
@@ -121,6 +129,13 @@ def test_ranks_that_select_different_prompts_reduce_in_the_same_order():
     check_against_single_process(run_two_ranks(flags, bucket_mb=1e-6), flags)
     # an UNDECLARED data-dependent parameter only costs overlap (the cursor waits for finish()), never correctness
     check_against_single_process(run_two_ranks(flags, bucket_mb=1e-6, declare=False), flags)
+
+
+def test_parameters_declared_end_of_backward_are_reduced_with_the_late_buckets():
+    """model.end_of_backward_parameters() (the real model: the FiLM MLPs, whose gradients all come from one autograd node at the
+    end of backward) joins the late set: same gradients, same launch order on both ranks."""
+    flags = (1, 0, 0, 1)
+    check_against_single_process(run_two_ranks(flags, bucket_mb=1e-6, head_late=True), flags)
 
 
 def test_single_rank_engine_is_a_noop():
