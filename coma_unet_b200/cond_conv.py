@@ -80,9 +80,10 @@ class FilmBatch:
         FilmBatch.active = {id(m): (out[l, :, :m.out_channels], out[l, :, cmax:cmax + m.out_channels])
                             for l, m in enumerate(self.mods)}
 
-    def compute_train(self, covariate):
-        """Under autograd: the same slices from ONE fused launch each way (ops.FilmAllFn) instead of a Linear -> ReLU -> Linear
-        chain per layer (~185 framework launches per training step of the north-star model).  False = not applicable."""
+    def compute_fused(self, covariate):
+        """The same slices from ONE fused launch (ops.FilmAllFn; one more in backward) instead of a Linear -> ReLU -> Linear chain
+        per layer under autograd (~185 framework launches per training step of the north-star model) or two batched GEMMs plus
+        a strided-slice copy per layer without it.  False = not applicable."""
         c = covariate.reshape(covariate.shape[0], -1)
         if not (ops.FUSED_FILM and self.mods and c.is_cuda and c.dtype == torch.float32 and c.shape[0] <= 64
                 and len(self.mods) <= 32 and all(p.dtype == torch.float32 for m in self.mods for p in m.film.parameters())):

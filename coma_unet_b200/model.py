@@ -171,8 +171,8 @@ class ObservableAttentionUnet(nn.Module):
         return self
 
     def _film_batch(self, covariate):
-        """Evaluate every FiLM MLP up front (cond_conv.FilmBatch): two batched GEMMs without autograd, one fused launch each way
-        (ops.FilmAllFn) with it."""
+        """Evaluate every FiLM MLP up front (cond_conv.FilmBatch): one fused launch (and one in backward, ops.FilmAllFn); with
+        COMA_DISABLE_FILM_FUSED=1 two batched GEMMs in no-grad mode and the per-layer modules under autograd."""
         if covariate is None or not self.conditional:
             return False
         fb = getattr(self, "_fb", None)
@@ -180,8 +180,10 @@ class ObservableAttentionUnet(nn.Module):
             fb = self._fb = cond_conv.FilmBatch(self)
         if covariate.shape[-1] < max((m.num_covars for m in fb.mods), default=0):
             return False
+        if fb.compute_fused(covariate):        # one launch, contiguous per-layer outputs -- with or without autograd
+            return True
         if torch.is_grad_enabled():
-            return fb.compute_train(covariate)
+            return False
         fb.compute(covariate)
         return True
 

@@ -130,7 +130,7 @@ PACK_KERNEL = os.environ.get("COMA_DISABLE_PACK_KERNEL", "0") != "1"
 
 def _layout_kernel_ok(w: torch.Tensor, dtype: torch.dtype) -> bool:
     return (PACK_KERNEL and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 5
-            and w.shape[2] * w.shape[3] * w.shape[4] <= 27 and dtype in (torch.float32, torch.bfloat16))
+            and w.shape[2] == w.shape[3] == w.shape[4] and w.shape[2] ** 3 <= 27 and dtype in (torch.float32, torch.bfloat16))
 
 
 def _weight_layout(param, packed, swap=False, flip=False, unpack=False):
