@@ -72,15 +72,44 @@ __global__ void __launch_bounds__(kFilmThreads) film_bwd_kernel(const __grid_con
     for (int b = 0; b < B; ++b) s = fmaf(dout[b * 2 * C + o], hid[b * FH + j], s);
     a.dW2[l][i] = s;
   }
-  // through the ReLU: dhid[b][j] = (hid > 0) * sum_o dout[b][o] W2[o][j]
+  // through the ReLU: dhid[b][j] = (hid > 0) * sum_o dout[b][o] W2[o][j].  W2 (up to 128 KB) was last touched in the forward pass,
+  // a whole step ago: the loads come from HBM, so they are spread over the warps (warp w owns the rows o = w, w + 8, ..., a lane
+  // the columns lane and lane + 32) and unrolled 8 deep -- 16 loads in flight per thread instead of a 512-long chain per thread
+  // (157 us for the 256-channel layer before).
   const float* W2 = a.W2[l];
-  for (int i = threadIdx.x; i < B * FH; i += kFilmThreads) {
-    const int b = i / FH, j = i - b * FH;
-    float s = 0.f;
-    for (int o = 0; o < 2 * C; ++o) s = fmaf(dout[b * 2 * C + o], __ldg(W2 + (size_t)o * FH + j), s);
-    dhid[i] = hid[i] > 0.f ? s : 0.f;
+  float* part = dout + B * 2 * C;                     // [8 warps][4][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    float acc[4][2];
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) acc[bb][0] = acc[bb][1] = 0.f;
+#pragma unroll 8
+    for (int o = warp; o < 2 * C; o += 8) {
+      const float wa = __ldg(W2 + (size_t)o * FH + lane), wb = __ldg(W2 + (size_t)o * FH + lane + 32);
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const float d = b0 + bb < B ? dout[(b0 + bb) * 2 * C + o] : 0.f;
+        acc[bb][0] = fmaf(d, wa, acc[bb][0]);
+        acc[bb][1] = fmaf(d, wb, acc[bb][1]);
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      part[(warp * 4 + bb) * FH + lane] = acc[bb][0];
+      part[(warp * 4 + bb) * FH + lane + 32] = acc[bb][1];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * FH; i += kFilmThreads) {
+      const int bb = i / FH, j = i - bb * FH;
+      if (b0 + bb < B) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[(w * 4 + bb) * FH + j];
+        dhid[(b0 + bb) * FH + j] = hid[(b0 + bb) * FH + j] > 0.f ? t : 0.f;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // first Linear: db1[j] = sum_b dhid[b][j], dW1[j][k] = sum_b dhid[b][j] cov[b][k]
   for (int j = threadIdx.x; j < FH; j += kFilmThreads) {
     float s = 0.f;
@@ -107,7 +136,7 @@ int check_film(const coma_film_args* a, bool bwd, size_t* smem) {
     else COMA_CHECK_ARG(a->out[l] != nullptr, "coma_film_mlp_fwd: layer %d: null output", l);
     cmax = a->C[l] > cmax ? a->C[l] : cmax;
   }
-  *smem = (size_t)a->B * FH * sizeof(float) * (bwd ? 2 : 1) + (bwd ? (size_t)a->B * 2 * cmax * sizeof(float) : 0);
+  *smem = (size_t)a->B * FH * sizeof(float) * (bwd ? 2 : 1) + (bwd ? ((size_t)a->B * 2 * cmax + 8 * 4 * FH) * sizeof(float) : 0);
   COMA_CHECK_ARG(*smem <= 200 * 1024, "coma_film_mlp: batch x channels too large for one block's shared memory");
   return COMA_OK;
 }
