@@ -151,3 +151,36 @@ def test_roi_table_and_prompt_declarations():
     film = [p for name, p in m.named_parameters() if ".film." in name]
     assert film and {id(p) for p in late} == {id(p) for p in film}
     assert not {id(p) for p in late} & {id(p) for p in dd}
+
+
+def _layout_as_documented(param, R_pad, C_pad, swap, flip):
+    """include/coma_b200.h, coma_weight_layout: packed[t][r][c] = param[a][b][t'] with (a, b) = (r, c) or, with swap, (c, r),
+    t' = T - 1 - t with flip, zero beyond A / B."""
+    import numpy as np
+    A, B, T = param.shape
+    out = np.zeros((T, R_pad, C_pad), param.dtype)
+    for t in range(T):
+        ts = T - 1 - t if flip else t
+        blk = param[:, :, ts].T if swap else param[:, :, ts]
+        out[t, :min(R_pad, blk.shape[0]), :min(C_pad, blk.shape[1])] = blk[:R_pad, :C_pad]
+    return out
+
+
+@pytest.mark.parametrize("transposed,stride", [(False, 1), (False, 2), (True, 2)])
+def test_weight_layout_abi_documentation_matches_the_tensor_op_chain(transposed, stride):
+    """The swap / flip table in the header against ops.pack_weight / pack_adjoint / unpack_weight_gradient on CPU tensors (the
+    chain of tensor ops; the GPU suite pins the kernel to the same chain bit for bit)."""
+    import numpy as np
+    torch.manual_seed(0)
+    cout, cin, k = 5, 3, 3
+    w = torch.randn((cin, cout, k, k, k) if transposed else (cout, cin, k, k, k))
+    flat = w.reshape(w.shape[0], w.shape[1], -1).numpy()
+    fwd = ops.pack_weight(w, transposed, 16, 16, torch.float32).numpy()
+    assert np.array_equal(fwd, _layout_as_documented(flat, 16, 16, swap=transposed, flip=False))
+    adj = ops.pack_adjoint(w, transposed, stride, 16, 16, 16, torch.float32).numpy()
+    assert np.array_equal(adj, _layout_as_documented(flat, 16, 16, swap=not transposed, flip=(not transposed and stride == 1)))
+    dwp = torch.randn(k ** 3, 16, 16)
+    dw = ops.unpack_weight_gradient(dwp, w)
+    assert dw.shape == w.shape
+    A, B = w.shape[0], w.shape[1]
+    assert np.array_equal(dw.reshape(A, B, -1).numpy(), dwp[:, :A, :B].permute(1, 2, 0).numpy())
