@@ -51,3 +51,19 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert b"coma_conv3d_fprop" in L.coma_last_error()
     a = _lib.ConvArgs()
     assert L.coma_conv3d_fprop(ctypes.byref(a), None) != 0
+    # round-2 entry points: argument checks come before any launch, so they run without a GPU
+    w = _lib.WeightLayoutArgs()
+    assert L.coma_weight_layout(ctypes.byref(w), None) != 0 and b"coma_weight_layout" in L.coma_last_error()
+    buf = (ctypes.c_float * 64)()
+    w.param = w.packed = ctypes.cast(buf, ctypes.c_void_p)
+    w.A, w.B, w.T, w.R_pad, w.C_pad = 1, 1, 64, 16, 16            # more than 27 taps
+    assert L.coma_weight_layout(ctypes.byref(w), None) != 0 and b"taps" in L.coma_last_error()
+    f = _lib.FilmArgs()
+    assert L.coma_film_mlp_fwd(ctypes.byref(f), None) != 0 and b"coma_film_mlp" in L.coma_last_error()
+    f.cov = f.hid = ctypes.cast(buf, ctypes.c_void_p)
+    f.n_layers, f.B, f.cov_stride = _lib.FILM_MAX_LAYERS + 1, 4, 6
+    assert L.coma_film_mlp_bwd(ctypes.byref(f), None) != 0
+    f.n_layers = 1                                                 # a layer without parameters
+    assert L.coma_film_mlp_fwd(ctypes.byref(f), None) != 0 and b"layer 0" in L.coma_last_error()
+    g = _lib.WgradArgs()
+    assert L.coma_conv3d_wgrad_workspace_size(ctypes.byref(g)) == 0
